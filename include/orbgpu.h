@@ -1,0 +1,186 @@
+/* orbgpu.h — C ABI of the B200-native ORB front-end (liborbgpu.so).
+ *
+ * Drop-in boundary for the ONE hot path of sjulier/Refactored_ORB_SLAM2 (paths below are relative
+ * to Source/Libraries/ORB_SLAM2 in the reference tree):
+ *
+ *   ORBextractor::operator()            src/ORBextractor.cc:978-1039   (include/ORBextractor.h:47-57)
+ *   ORBextractor getters / tables       include/ORBextractor.h:59-75, src/ORBextractor.cc:407-464
+ *   ORBmatcher::DescriptorDistance +    src/ORBmatcher.cc:1542-1556, best/second-best loops :201-243
+ *     the best / second-best searches
+ *   Frame::ComputeStereoMatches         src/Frame.cc:477-646
+ *
+ * Plain pointers and sizes only; no C++/torch types.  Every entry point returns ORBGPU_OK (0) or a
+ * negative error code; orbgpu_last_error() returns the message for the calling thread.  Nothing in
+ * this library falls back to the CPU: without a usable CUDA device every compute call fails with
+ * ORBGPU_E_CUDA.
+ *
+ * Threading: one handle = one CUDA stream + private device buffers.  Distinct handles may be used
+ * concurrently from distinct host threads (the reference runs the left and right extractor on two
+ * std::threads, src/Frame.cc:87-90); one handle must not be used from two threads at once.
+ */
+#ifndef ORBGPU_H
+#define ORBGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBGPU_VERSION 100
+
+enum {
+  ORBGPU_OK = 0,
+  ORBGPU_E_INVALID = -1,     /* bad argument */
+  ORBGPU_E_CUDA = -2,        /* CUDA runtime error, or no device */
+  ORBGPU_E_CAPACITY = -3,    /* a caller- or handle-sized buffer is too small */
+  ORBGPU_E_UNSUPPORTED = -4  /* shape the reference itself cannot process (e.g. aspect < 0.5) */
+};
+
+/* cv::KeyPoint memory layout (7 x 4 bytes): pt.x, pt.y, size, angle, response, octave, class_id. */
+typedef struct orbgpu_keypoint {
+  float x, y, size, angle, response;
+  int32_t octave, class_id;
+} orbgpu_keypoint;
+
+/* ORBextractor constructor arguments (include/ORBextractor.h:50-51) + device buffer sizing. */
+typedef struct orbgpu_extractor_params {
+  int32_t nfeatures;
+  float scale_factor;
+  int32_t nlevels;
+  int32_t ini_th_fast;
+  int32_t min_th_fast;
+  int32_t max_width;   /* largest image the handle will see */
+  int32_t max_height;
+  int32_t max_batch;   /* images processed per call (a stereo pair = 2) */
+  int32_t device;      /* CUDA device ordinal, -1 = current device */
+} orbgpu_extractor_params;
+
+typedef struct orbgpu_extractor orbgpu_extractor;
+typedef struct orbgpu_bank orbgpu_bank;
+
+int orbgpu_version(void);
+const char *orbgpu_last_error(void);
+int orbgpu_device_count(void);
+
+/* ---- ORBextractor ------------------------------------------------------------------------- */
+
+/* ORBextractor::ORBextractor (src/ORBextractor.cc:407-464). */
+int orbgpu_extractor_create(const orbgpu_extractor_params *params, orbgpu_extractor **out);
+void orbgpu_extractor_destroy(orbgpu_extractor *e);
+
+/* GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares
+ * (include/ORBextractor.h:63-73) and mnFeaturesPerLevel; each array holds nlevels entries, any
+ * pointer may be NULL. */
+int orbgpu_extractor_tables(const orbgpu_extractor *e, float *scale, float *inv_scale, float *sigma2,
+                            float *inv_sigma2, int32_t *features_per_level);
+/* Upper bound on keypoints per image: sum of per-level quotas + 3 per level (a careful octree split
+ * adds at most 3 nodes before the >= N break, src/ORBextractor.cc:701-702). */
+int orbgpu_extractor_capacity(const orbgpu_extractor *e);
+
+/* ORBextractor::operator()(image, mask, keypoints, descriptors) (src/ORBextractor.cc:978-1039):
+ * one CV_8UC1 host image with row stride `step`; mask is ignored by the reference and absent here.
+ * Writes *n keypoints (level-major, reference order) and *n rows of 32 descriptor bytes.
+ * An empty image (width or height 0, or image NULL) returns ORBGPU_OK with *n = 0, like :981. */
+int orbgpu_extract(orbgpu_extractor *e, const uint8_t *image, int width, int height, size_t step,
+                   orbgpu_keypoint *keypoints, uint8_t *descriptors, int capacity, int *n);
+
+/* The same call over `count` equally sized host images (image i starts at images + i*image_step).
+ * keypoints / descriptors hold `capacity` rows per image; counts[i] receives image i's count. */
+int orbgpu_extract_batch(orbgpu_extractor *e, const uint8_t *images, int count, int width, int height,
+                         size_t row_step, size_t image_step, orbgpu_keypoint *keypoints,
+                         uint8_t *descriptors, int capacity, int32_t *counts);
+
+/* Device-resident form: images already in HBM; results stay in the handle's device buffers (see
+ * orbgpu_results_device) until the next extract call.  Asynchronous on the handle's stream. */
+int orbgpu_extract_batch_device(orbgpu_extractor *e, const uint8_t *d_images, int count, int width,
+                                int height, size_t row_step, size_t image_step);
+/* Device pointers to the last batch: keypoints [count][capacity], descriptors [count][capacity][32],
+ * counts [count].  *capacity receives the row capacity per image. */
+int orbgpu_results_device(orbgpu_extractor *e, const orbgpu_keypoint **d_keypoints,
+                          const uint8_t **d_descriptors, const int32_t **d_counts, int *capacity);
+/* Copies the last batch's results to host buffers laid out as in orbgpu_extract_batch; checks the
+ * device-side status word (candidate / node capacity) and synchronises the stream. */
+int orbgpu_download_results(orbgpu_extractor *e, orbgpu_keypoint *keypoints, uint8_t *descriptors,
+                            int capacity, int32_t *counts);
+int orbgpu_synchronize(orbgpu_extractor *e);
+/* The handle's cudaStream_t (as void*), so callers can order their own work against it. */
+void *orbgpu_extractor_stream(orbgpu_extractor *e);
+
+/* mvImagePyramid (include/ORBextractor.h:75): level size and bytes of image `image` of the last
+ * batch.  with_border != 0 also copies the 19 px BORDER_REFLECT_101 apron (dst is then
+ * (h+38) x (w+38)). */
+int orbgpu_level_size(const orbgpu_extractor *e, int level, int *width, int *height);
+int orbgpu_get_pyramid_level(orbgpu_extractor *e, int image, int level, int with_border, uint8_t *dst,
+                             size_t dst_step);
+/* Stage outputs for parity tests: stage 0 = FAST candidates after per-cell NMS (returned sorted in
+ * the reference's cell-major order), 1 = octree selection in list order, 2 = blurred level bytes
+ * are fetched with orbgpu_get_blurred_level.  Rows are (x, y, response) in octree coordinates
+ * (level coordinates - 16).  Returns the row count (>= 0) or an error code. */
+int orbgpu_get_stage(orbgpu_extractor *e, int image, int level, int stage, int32_t *rows, int capacity);
+int orbgpu_get_blurred_level(orbgpu_extractor *e, int image, int level, uint8_t *dst, size_t dst_step);
+
+/* ---- Frame::ComputeStereoMatches ------------------------------------------------------------ */
+
+/* Frame::ComputeStereoMatches (src/Frame.cc:477-646) for `pairs` stereo pairs whose left images are
+ * images [first_left, first_left+pairs) of `left`'s last batch and right images are
+ * [first_right, ...) of `right`'s last batch (left and right may be the same handle).
+ * `mb` is the baseline in metres (= mbf / fx): the reference reads the member before assigning it
+ * (src/Frame.cc:505 vs :124), so it is explicit here.  u_right / depth hold `capacity` floats per
+ * pair (host memory), -1 where there is no match (mvuRight / mvDepth). */
+int orbgpu_stereo_match(orbgpu_extractor *left, orbgpu_extractor *right, int first_left,
+                        int first_right, int pairs, float mbf, float mb, float *u_right, float *depth,
+                        int capacity);
+/* Device-resident form; results at orbgpu_stereo_results_device of the LEFT handle. */
+int orbgpu_stereo_match_device(orbgpu_extractor *left, orbgpu_extractor *right, int first_left,
+                               int first_right, int pairs, float mbf, float mb);
+int orbgpu_stereo_results_device(orbgpu_extractor *left, const float **d_u_right, const float **d_depth,
+                                 const int32_t **d_best_sad);
+
+/* ---- ORBmatcher Hamming searches ------------------------------------------------------------ */
+
+/* ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1542-1556) for n pairs of 32-byte rows (host). */
+int orbgpu_descriptor_distance(const uint8_t *a, const uint8_t *b, int n, int32_t *dist, int device);
+
+/* A descriptor bank (keyframe descriptors) resident in HBM.  `index_base` is added to row numbers
+ * in results, so a row-sharded bank reports global indices. */
+int orbgpu_bank_create(const uint8_t *descriptors, int rows, int64_t index_base, int device,
+                       orbgpu_bank **out);
+/* Wraps device memory owned by the caller (must stay alive, 16-byte aligned). */
+int orbgpu_bank_wrap_device(const uint8_t *d_descriptors, int rows, int64_t index_base, int device,
+                            orbgpu_bank **out);
+void orbgpu_bank_destroy(orbgpu_bank *b);
+
+/* Best / second-best scan of src/ORBmatcher.cc:201-221 over the whole bank for every query:
+ * strict '<' (lowest index wins ties), best1 = best2 = 256 and idx = -1 when the bank is empty.
+ * Host queries [nq][32]; outputs idx1 (int64, global index), d1, d2 (int32). */
+int orbgpu_hamming_top2_dense(orbgpu_bank *bank, const uint8_t *queries, int nq, int64_t *idx1,
+                              int32_t *d1, int32_t *d2);
+/* Device form: d_queries [nq][32] (16-byte aligned); d_result receives nq records of
+ * { int32 d1, int32 d2, int64 idx1 } (16 bytes) — the unit exchanged between bank shards. */
+int orbgpu_hamming_top2_dense_device(orbgpu_bank *bank, const uint8_t *d_queries, int nq,
+                                     void *d_result, void *stream);
+/* Merges `parts` shard results ([parts][nq] records, shard order = ascending bank index) exactly
+ * as one sequential scan over the concatenated bank would; optionally applies the acceptance test
+ * of src/ORBmatcher.cc:224-226 (d1 <= th_low && d1 < nnratio*d2): d_match[i] = idx1 or -1. */
+int orbgpu_top2_merge_device(const void *d_parts, int parts, int nq, void *d_result, float nnratio,
+                             int th_low, int64_t *d_match, int device, void *stream);
+
+/* Candidate-list form used by the projection / BoW searches: query i scans train rows
+ * cand[offsets[i] .. offsets[i+1]) in list order.  Host pointers; idx1 is a train row or -1. */
+int orbgpu_hamming_top2_csr(const uint8_t *queries, int nq, const uint8_t *train, int nt,
+                            const int32_t *offsets, const int32_t *cand, int32_t *idx1, int32_t *d1,
+                            int32_t *d2, int device);
+
+/* Measured integer-pipe peak (register-resident POPC loop): returns POPC lane-ops per second. */
+int orbgpu_measure_popc_peak(int device, double *popc_per_second, double *lop3_per_second);
+
+/* Kernel launches issued by this library on the calling thread since the last reset (bench's
+ * gpu_launches counter). */
+int64_t orbgpu_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBGPU_H */

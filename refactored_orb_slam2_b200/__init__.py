@@ -1,0 +1,10 @@
+"""refactored_orb_slam2_b200 — the ORB front-end of sjulier/Refactored_ORB_SLAM2 as hand-written
+sm_100a CUDA kernels behind a C ABI (include/orbgpu.h) and a host-side mirror of the reference's
+ORBextractor / ORBmatcher / Frame::ComputeStereoMatches interfaces.  No CPU fallback."""
+from ._lib import KP_DTYPE, TOP2_DTYPE, OrbGpuError, lib  # noqa: F401
+from .extractor import ORBextractor  # noqa: F401
+from .matcher import DescriptorBank, ORBmatcher, merge_top2_device  # noqa: F401
+from .stereo import ComputeStereoMatches, Frame  # noqa: F401
+
+__all__ = ["ORBextractor", "ORBmatcher", "DescriptorBank", "ComputeStereoMatches", "Frame", "merge_top2_device",
+           "KP_DTYPE", "TOP2_DTYPE", "OrbGpuError", "lib"]

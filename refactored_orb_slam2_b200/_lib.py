@@ -1,0 +1,98 @@
+"""ctypes binding of liborbgpu.so (the C ABI in include/orbgpu.h).
+
+The library is the product: there is no CPU fallback anywhere in this package.  If the shared
+object has not been built (``python -c 'import __graft_entry__ as g; g.build()'`` or
+``make -C refactored_orb_slam2_b200/csrc``) importing a compute entry point raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liborbgpu.so")
+
+OK, E_INVALID, E_CUDA, E_CAPACITY, E_UNSUPPORTED = 0, -1, -2, -3, -4
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])   # cv::KeyPoint, 28 bytes
+TOP2_DTYPE = np.dtype([("d1", "<i4"), ("d2", "<i4"), ("idx", "<i8")])                # shard exchange record, 16 bytes
+assert KP_DTYPE.itemsize == 28 and TOP2_DTYPE.itemsize == 16
+
+
+class ExtractorParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("max_width", C.c_int32),
+                ("max_height", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32)]
+
+
+class OrbGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("orbgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+# every symbol include/orbgpu.h declares: name -> (restype, argtypes)
+_vp, _i, _f, _sz, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
+SYMBOLS = {
+    "orbgpu_version": (_i, []),
+    "orbgpu_last_error": (C.c_char_p, []),
+    "orbgpu_device_count": (_i, []),
+    "orbgpu_extractor_create": (_i, [C.POINTER(ExtractorParams), C.POINTER(_vp)]),
+    "orbgpu_extractor_destroy": (None, [_vp]),
+    "orbgpu_extractor_tables": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "orbgpu_extractor_capacity": (_i, [_vp]),
+    "orbgpu_extract": (_i, [_vp, _vp, _i, _i, _sz, _vp, _vp, _i, C.POINTER(_i)]),
+    "orbgpu_extract_batch": (_i, [_vp, _vp, _i, _i, _i, _sz, _sz, _vp, _vp, _i, _vp]),
+    "orbgpu_extract_batch_device": (_i, [_vp, _vp, _i, _i, _i, _sz, _sz]),
+    "orbgpu_results_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i)]),
+    "orbgpu_download_results": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "orbgpu_synchronize": (_i, [_vp]),
+    "orbgpu_extractor_stream": (_vp, [_vp]),
+    "orbgpu_level_size": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "orbgpu_get_pyramid_level": (_i, [_vp, _i, _i, _i, _vp, _sz]),
+    "orbgpu_get_stage": (_i, [_vp, _i, _i, _i, _vp, _i]),
+    "orbgpu_get_blurred_level": (_i, [_vp, _i, _i, _vp, _sz]),
+    "orbgpu_stereo_match": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _i]),
+    "orbgpu_stereo_match_device": (_i, [_vp, _vp, _i, _i, _i, _f, _f]),
+    "orbgpu_stereo_results_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "orbgpu_descriptor_distance": (_i, [_vp, _vp, _i, _vp, _i]),
+    "orbgpu_bank_create": (_i, [_vp, _i, _i64, _i, C.POINTER(_vp)]),
+    "orbgpu_bank_wrap_device": (_i, [_vp, _i, _i64, _i, C.POINTER(_vp)]),
+    "orbgpu_bank_destroy": (None, [_vp]),
+    "orbgpu_hamming_top2_dense": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "orbgpu_hamming_top2_dense_device": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "orbgpu_top2_merge_device": (_i, [_vp, _i, _i, _vp, _f, _i, _vp, _i, _vp]),
+    "orbgpu_hamming_top2_csr": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i]),
+    "orbgpu_measure_popc_peak": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "orbgpu_launch_count": (_i64, [_i]),
+}
+
+_LIB = None
+
+
+def lib():
+    """Loads liborbgpu.so once; raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing: build it with `make -C %s/csrc` (or __graft_entry__.build()); "
+                              "this package has no CPU fallback" % (LIB_PATH, _HERE))
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)      # AttributeError if the ABI and the header drifted apart
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(rc):
+    if rc < 0:
+        raise OrbGpuError(rc, lib().orbgpu_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def ptr(a):
+    """void* of a numpy array (or None)."""
+    return None if a is None else a.ctypes.data_as(C.c_void_p)

@@ -1,0 +1,191 @@
+// Orientation, descriptor and output assembly: IC_Angle / computeOrientation
+// (ORBextractor.cc:76-100, 466-473), computeOrbDescriptor (ORBextractor.cc:102-146) and the
+// tail of ORBextractor::operator() (ORBextractor.cc:1023-1037).
+//
+// One warp = one keypoint.
+//  * IC_Angle: 31 coalesced row reads of the UNBLURRED level (lane = column u), integer moments
+//    m10 / m01 reduced by shuffles (exact, order-free), then cv::fastAtan2's float polynomial with
+//    round-to-nearest mul/add/div intrinsics (the reference build never fuses into FMAs).
+//  * rBRIEF: lane i builds descriptor byte i from 16 pattern points rotated by (cos, sin) of the
+//    angle.  cosf/sinf replicate glibc's double-precision sincosf algorithm (see sincos_glibc) so
+//    that cvRound(x*b + y*a) lands on the same pixel as on the host.
+//  * The keypoint record (cv::KeyPoint layout) and the 32-byte descriptor row go straight to their
+//    final, level-major slot: start = sum of the lower levels' octree counts.
+#include "internal.cuh"
+
+namespace orbgpu {
+
+namespace {
+
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};  // ORBextractor.cc:449-463
+__device__ const signed char d_pattern[1024] = {
+#include "../../include/orb_pattern.inc"
+};
+
+// cv::fastAtan2(y, x) scalar path (called at ORBextractor.cc:99): degrees in [0, 360).
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+  const float scale = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale,
+              p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+  const float eps = (float)2.2204460492503131e-16;
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+// glibc >= 2.28 sinf/cosf/sincosf (ARM optimized-routines algorithm): everything in double,
+// Cody-Waite reduction by pi/2 for |x| < 120, degree-7/8 polynomials, one rounding to float.
+// Only the |x| < 120 range is needed: angles are fastAtan2 degrees * pi/180 in [0, 2*pi].
+__device__ __forceinline__ float sincos_poly(double x, double x2, bool neg, bool cosine) {
+  const double C0 = neg ? -1.0 : 1.0;
+  const double C1 = neg ? 0x1.ffffffd0c621cp-2 : -0x1.ffffffd0c621cp-2;
+  const double C2 = neg ? -0x1.55553e1068f19p-5 : 0x1.55553e1068f19p-5;
+  const double C3 = neg ? 0x1.6c087e89a359dp-10 : -0x1.6c087e89a359dp-10;
+  const double C4 = neg ? -0x1.99343027bf8c3p-16 : 0x1.99343027bf8c3p-16;
+  const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+  if (!cosine) {
+    const double x3 = __dmul_rn(x, x2);
+    const double s1 = __dadd_rn(S2, __dmul_rn(x2, S3));
+    const double x7 = __dmul_rn(x3, x2);
+    const double s = __dadd_rn(x, __dmul_rn(x3, S1));
+    return (float)__dadd_rn(s, __dmul_rn(x7, s1));
+  }
+  const double x4 = __dmul_rn(x2, x2);
+  const double c2 = __dadd_rn(C3, __dmul_rn(x2, C4));
+  const double c1 = __dadd_rn(C0, __dmul_rn(x2, C1));
+  const double x6 = __dmul_rn(x4, x2);
+  const double c = __dadd_rn(c1, __dmul_rn(x4, C2));
+  return (float)__dadd_rn(c, __dmul_rn(x6, c2));
+}
+
+__device__ __forceinline__ void sincos_glibc(float y, float *sinp, float *cosp) {
+  const unsigned top = (__float_as_uint(y) >> 20) & 0x7ff;
+  double x = (double)y;
+  if (top < ((__float_as_uint(0x1.921FB6p-1f) >> 20) & 0x7ff)) {          // |y| < pi/4
+    if (top < ((__float_as_uint(0x1p-12f) >> 20) & 0x7ff)) { *sinp = y; *cosp = 1.0f; return; }
+    const double x2 = __dmul_rn(x, x);
+    *sinp = sincos_poly(x, x2, false, false);
+    *cosp = sincos_poly(x, x2, false, true);
+    return;
+  }
+  const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
+  const int n = ((int)r + 0x800000) >> 24;
+  x = __dsub_rn(x, __dmul_rn((double)n, 0x1.921FB54442D18p0));
+  const double sgn = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+  const bool neg = (n & 2) != 0;
+  const double xs = __dmul_rn(x, sgn), x2 = __dmul_rn(x, x);
+  *sinp = sincos_poly(xs, x2, neg, (n & 1) != 0);
+  *cosp = sincos_poly(xs, x2, neg, (n & 1) == 0);
+}
+
+constexpr int kWarpsPerCta = 8;
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur,
+           const int4 *__restrict__ selAll, const int *__restrict__ selCount, orbgpu_keypoint *__restrict__ kps,
+           uint8_t *__restrict__ desc, int *__restrict__ kpCount, unsigned *__restrict__ status) {
+  __shared__ signed char sPat[1024];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) sPat[i] = d_pattern[i];
+  __syncthreads();
+
+  const int level = blockIdx.y, img = blockIdx.z;
+  const LevelGeom &G = T->lv[level];
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const int *cnt = selCount + img * kMaxLevels;
+  int start = 0, total = 0;
+  for (int l = 0; l < T->nlevels; l++) {
+    const int c = cnt[l];
+    if (l < level) start += c;
+    total += c;
+  }
+  const int kpCap = T->kpCap;
+  if (level == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+    kpCount[img] = min(total, kpCap);
+    if (total > kpCap) atomicOr(status, kStatusKpOverflow);
+  }
+  if (k >= cnt[level] || start + k >= kpCap) return;
+
+  const int4 s = selAll[G.selOffset + (size_t)img * G.selCap + k];   // x_level, y_level, response
+  const size_t plane = G.pyrOffset + (size_t)img * G.planeBytes;
+  const uint8_t *centre = pyr + plane + (size_t)(s.y + kEdge) * G.pitch + (s.x + kEdge);
+
+  // ---- IC_Angle
+  int m10 = 0, m01 = 0;
+  const int u = lane - kHalfPatch;
+  if (lane < 31) {
+    const int au = abs(u);
+#pragma unroll 1
+    for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
+      if (au <= c_umax[abs(v)]) {
+        const int val = centre[v * G.pitch + u];
+        m10 += u * val;
+        m01 += v * val;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+    m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+  }
+  const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+  // ---- steered BRIEF on the blurred level
+  const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+  float a, b;
+  sincos_glibc(__fmul_rn(angle, factorPI), &b, &a);   // a = cos, b = sin
+  const uint8_t *bc = blur + plane + (size_t)(s.y + kEdge) * G.pitch + (s.x + kEdge);
+  const signed char *p = sPat + lane * 32;     // 16 pattern points (x, y) per descriptor byte
+  unsigned val = 0;
+#pragma unroll
+  for (int bit = 0; bit < 8; bit++, p += 4) {
+    int t[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const float px = (float)p[2 * e], py = (float)p[2 * e + 1];
+      const int ry = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+      const int rx = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+      t[e] = bc[ry * G.pitch + rx];
+    }
+    val |= (unsigned)(t[0] < t[1]) << bit;
+  }
+  const size_t row = (size_t)img * kpCap + start + k;
+  desc[row * 32 + lane] = (uint8_t)val;
+  if (lane == 0) {
+    orbgpu_keypoint o;
+    o.x = (float)s.x; o.y = (float)s.y;
+    if (level != 0) { o.x = __fmul_rn(o.x, G.scale); o.y = __fmul_rn(o.y, G.scale); }
+    o.size = (float)G.patchSize;
+    o.angle = angle;
+    o.response = (float)s.z;
+    o.octave = level;
+    o.class_id = -1;
+    kps[row] = o;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_describe(const LevelTable &T, const ExtractBuffers &B, int batch, cudaStream_t s) {
+  int maxSel = 1;
+  for (int l = 0; l < T.nlevels; l++) maxSel = max(maxSel, T.lv[l].selCap);
+  dim3 grid((maxSel + kWarpsPerCta - 1) / kWarpsPerCta, T.nlevels, batch);
+  k_describe<<<grid, kWarpsPerCta * 32, 0, s>>>(B.dT, B.pyr, B.blur, B.sel, B.selCount, B.kps, B.desc, B.kpCount,
+                                                B.status);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace orbgpu

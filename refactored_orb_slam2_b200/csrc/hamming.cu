@@ -1,0 +1,351 @@
+// ORBmatcher Hamming searches: DescriptorDistance (ORBmatcher.cc:1542-1556) and the
+// best / second-best scan every ORBmatcher search runs over its candidates (ORBmatcher.cc:201-221:
+// strict '<', so the first minimum in scan order wins; second = second-smallest of the multiset).
+//
+// Dense bank scan (BASELINE.json config 4: 2000 queries x 1M-row keyframe bank):
+//   * a CTA owns a contiguous chunk of bank rows and a tile of 256*Q queries; each consumer thread
+//     keeps Q query descriptors (8 words each) and their running (d1, idx1, d2) in registers;
+//   * a producer warp streams the chunk through a 4-stage shared-memory ring with TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx); consumers read each 32-byte row as two broadcast
+//     LDS.128 and release the stage through an "empty" mbarrier;
+//   * distance = carry-save compression of the 8 XOR words (two levels of 3:2 adders in LOP3) down
+//     to ones/ones/twos/fours words -> 4 POPC + 16 LOP3 per pair instead of 8 POPC + 8 LOP3, which
+//     rebalances work from the quarter-rate POPC unit to the ALU pipe (variant 0 keeps the naive
+//     8-POPC form for the roofline comparison);
+//   * the top-2 update sits behind one compare (d < d2), which is rarely true after warm-up;
+//   * every (chunk, query) emits a 16-byte record {d1, d2, idx}; a merge kernel folds chunks in
+//     ascending bank order, which is exactly what the sequential scan would have produced.  The
+//     same merge folds the per-GPU records of a row-sharded bank after the all-gather.
+#include <cstdlib>
+
+#include "internal.cuh"
+
+namespace orbgpu {
+
+namespace {
+
+constexpr int kConsumers = 256;
+constexpr int kDenseThreads = kConsumers + 32;   // + one producer warp
+constexpr int kTileRows = 128;
+constexpr int kStages = 4;
+constexpr int kTileBytes = kTileRows * 32;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int IMM>
+__device__ __forceinline__ unsigned lop3(unsigned a, unsigned b, unsigned c) {
+  unsigned d;
+  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(IMM));
+  return d;
+}
+
+template <int VARIANT>
+__device__ __forceinline__ int distance256(const unsigned (&q)[8], const uint4 b0, const uint4 b1) {
+  const unsigned x0 = q[0] ^ b0.x, x1 = q[1] ^ b0.y, x2 = q[2] ^ b0.z, x3 = q[3] ^ b0.w;
+  const unsigned x4 = q[4] ^ b1.x, x5 = q[5] ^ b1.y, x6 = q[6] ^ b1.z, x7 = q[7] ^ b1.w;
+  if (VARIANT == 0) {
+    return __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3) + __popc(x4) + __popc(x5) + __popc(x6) + __popc(x7);
+  } else {
+    const unsigned s0 = lop3<0x96>(x0, x1, x2), c0 = lop3<0xe8>(x0, x1, x2);
+    const unsigned s1 = lop3<0x96>(x3, x4, x5), c1 = lop3<0xe8>(x3, x4, x5);
+    const unsigned s2 = lop3<0x96>(s0, s1, x6), c2 = lop3<0xe8>(s0, s1, x6);
+    const unsigned s4 = lop3<0x96>(c0, c1, c2), c4 = lop3<0xe8>(c0, c1, c2);
+    return __popc(s2) + __popc(x7) + 2 * __popc(s4) + 4 * __popc(c4);
+  }
+}
+
+template <int Q, int VARIANT>
+__global__ void __launch_bounds__(kDenseThreads)
+k_hamming_dense(const uint8_t *__restrict__ bank, int rows, int chunkRows, long long indexBase,
+                const uint8_t *__restrict__ queries, int nq, Top2Rec *__restrict__ partial) {
+  __shared__ __align__(128) uint8_t sTile[kStages][kTileBytes];
+  __shared__ __align__(8) unsigned long long sFull[kStages], sEmpty[kStages];
+
+  const int tid = threadIdx.x;
+  const int chunk = blockIdx.x;
+  const int row0 = chunk * chunkRows;
+  const int nrows = max(0, min(chunkRows, rows - row0));
+  const int ntiles = (nrows + kTileRows - 1) / kTileRows;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; s++) { mbar_init(&sFull[s], 1); mbar_init(&sEmpty[s], kConsumers / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (tid >= kConsumers) {
+    // ---- producer warp: one elected lane keeps the ring full
+    if (tid == kConsumers) {
+      for (int t = 0; t < ntiles; t++) {
+        const int s = t % kStages;
+        if (t >= kStages) mbar_wait(&sEmpty[s], ((t / kStages) - 1) & 1);
+        const int r = min(kTileRows, nrows - t * kTileRows);
+        mbar_expect_tx(&sFull[s], (unsigned)r * 32u);
+        bulk_g2s(sTile[s], bank + ((size_t)row0 + (size_t)t * kTileRows) * 32, (unsigned)r * 32u, &sFull[s]);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers
+  const int qBase = blockIdx.y * (kConsumers * Q);
+  unsigned q[Q][8];
+  int d1[Q], d2[Q], i1[Q];
+#pragma unroll
+  for (int j = 0; j < Q; j++) {
+    const int qi = qBase + j * kConsumers + tid;
+    d1[j] = 256; d2[j] = 256; i1[j] = -1;
+    if (qi < nq) {
+      const uint4 a = reinterpret_cast<const uint4 *>(queries)[2 * (size_t)qi];
+      const uint4 b = reinterpret_cast<const uint4 *>(queries)[2 * (size_t)qi + 1];
+      q[j][0] = a.x; q[j][1] = a.y; q[j][2] = a.z; q[j][3] = a.w;
+      q[j][4] = b.x; q[j][5] = b.y; q[j][6] = b.z; q[j][7] = b.w;
+    } else {
+#pragma unroll
+      for (int w = 0; w < 8; w++) q[j][w] = 0;
+    }
+  }
+  for (int t = 0; t < ntiles; t++) {
+    const int s = t % kStages;
+    mbar_wait(&sFull[s], (t / kStages) & 1);
+    const uint4 *tile = reinterpret_cast<const uint4 *>(sTile[s]);
+    const int r = min(kTileRows, nrows - t * kTileRows);
+    const int rowIdx0 = t * kTileRows;
+#pragma unroll 2
+    for (int i = 0; i < r; i++) {
+      const uint4 b0 = tile[2 * i], b1 = tile[2 * i + 1];
+#pragma unroll
+      for (int j = 0; j < Q; j++) {
+        const int d = distance256<VARIANT>(q[j], b0, b1);
+        if (d < d2[j]) {
+          if (d < d1[j]) { d2[j] = d1[j]; d1[j] = d; i1[j] = rowIdx0 + i; }
+          else d2[j] = d;
+        }
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&sEmpty[s]);
+  }
+#pragma unroll
+  for (int j = 0; j < Q; j++) {
+    const int qi = qBase + j * kConsumers + tid;
+    if (qi < nq) {
+      Top2Rec o;
+      o.d1 = d1[j]; o.d2 = d2[j];
+      o.idx = i1[j] < 0 ? -1ll : indexBase + row0 + i1[j];
+      partial[(size_t)chunk * nq + qi] = o;
+    }
+  }
+}
+
+// Folds `nparts` records per query in ascending part order == ascending bank index.
+__global__ void k_top2_merge(const Top2Rec *__restrict__ parts, int nparts, int nq, Top2Rec *__restrict__ result,
+                             float nnratio, int thLow, long long *__restrict__ match) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  int d1 = 256, d2 = 256;
+  long long idx = -1;
+  for (int p = 0; p < nparts; p++) {
+    const Top2Rec r = parts[(size_t)p * nq + qi];
+    if (r.d1 < d1) { d2 = min(d1, r.d2); d1 = r.d1; idx = r.idx; }
+    else d2 = min(d2, r.d1);
+  }
+  if (result) { Top2Rec o; o.d1 = d1; o.d2 = d2; o.idx = idx; result[qi] = o; }
+  if (match) {
+    // ORBmatcher.cc:224-226
+    const bool ok = d1 <= thLow && (float)d1 < __fmul_rn(nnratio, (float)d2);
+    match[qi] = ok ? idx : -1ll;
+  }
+}
+
+// Candidate-list scan: one warp per query, lanes stride the list; merge keeps list order semantics.
+__global__ void k_hamming_csr(const uint8_t *__restrict__ queries, int nq, const uint8_t *__restrict__ train,
+                              const int *__restrict__ offsets, const int *__restrict__ cand, int *__restrict__ idx1,
+                              int *__restrict__ od1, int *__restrict__ od2) {
+  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (qi >= nq) return;
+  const uint4 a0 = reinterpret_cast<const uint4 *>(queries)[2 * (size_t)qi];
+  const uint4 a1 = reinterpret_cast<const uint4 *>(queries)[2 * (size_t)qi + 1];
+  const int lo = offsets[qi], hi = offsets[qi + 1];
+  int d1 = 256, d2 = 256, p1 = 0x7fffffff;
+  for (int p = lo + lane; p < hi; p += 32) {
+    const uint4 *t = reinterpret_cast<const uint4 *>(train) + 2 * (size_t)cand[p];
+    const uint4 b0 = t[0], b1 = t[1];
+    const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                  __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+    if (d < d1) { d2 = d1; d1 = d; p1 = p; }
+    else if (d < d2) d2 = d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int e1 = __shfl_xor_sync(0xffffffffu, d1, o);
+    const int e2 = __shfl_xor_sync(0xffffffffu, d2, o);
+    const int q1 = __shfl_xor_sync(0xffffffffu, p1, o);
+    if (e1 < d1 || (e1 == d1 && q1 < p1)) { d2 = min(d1, e2); d1 = e1; p1 = q1; }
+    else d2 = min(d2, e1);
+  }
+  if (lane == 0) {
+    idx1[qi] = d1 < 256 ? cand[p1] : -1;
+    od1[qi] = d1;
+    od2[qi] = d2;
+  }
+}
+
+__global__ void k_pair_distance(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, int n, int *__restrict__ dist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned *pa = reinterpret_cast<const unsigned *>(a) + 8 * (size_t)i;
+  const unsigned *pb = reinterpret_cast<const unsigned *>(b) + 8 * (size_t)i;
+  int d = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) d += __popc(pa[w] ^ pb[w]);
+  dist[i] = d;
+}
+
+// Register-resident issue-rate probes: 8 independent dependency chains per thread.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_pipe_probe(unsigned *out, int iters, unsigned seed) {
+  unsigned v[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) v[j] = seed * (threadIdx.x + 1) + j * 0x9e3779b9u;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        if (MODE == 0) asm volatile("popc.b32 %0, %0;" : "+r"(v[j]));
+        else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(seed), "r"(i));
+      }
+    }
+  }
+  unsigned acc = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) acc ^= v[j];
+  if (acc == 0x12345678u) out[0] = acc;
+}
+
+}  // namespace
+
+int hamming_dense_q(int nq) { return nq > 4 * kConsumers ? 8 : nq > 2 * kConsumers ? 4 : nq > kConsumers ? 2 : 1; }
+
+int hamming_dense_chunks(int rows, int nq, int smCount) {
+  const int Q = hamming_dense_q(nq);
+  const int qTiles = (nq + kConsumers * Q - 1) / (kConsumers * Q);
+  int chunks = max(1, (2 * smCount + qTiles - 1) / qTiles);
+  int chunkRows = max((rows + chunks - 1) / chunks, kTileRows);
+  return max(1, (rows + chunkRows - 1) / chunkRows);
+}
+
+template <int Q>
+static void launch_dense_q(int variant, dim3 grid, cudaStream_t s, const uint8_t *bank, int rows, int chunkRows,
+                           long long indexBase, const uint8_t *q, int nq, Top2Rec *partial) {
+  if (variant == 0)
+    k_hamming_dense<Q, 0><<<grid, kDenseThreads, 0, s>>>(bank, rows, chunkRows, indexBase, q, nq, partial);
+  else
+    k_hamming_dense<Q, 1><<<grid, kDenseThreads, 0, s>>>(bank, rows, chunkRows, indexBase, q, nq, partial);
+}
+
+cudaError_t launch_hamming_dense(const uint8_t *bank, int rows, long long indexBase, const uint8_t *q,
+                                 int nq, Top2Rec *partial, int chunks, Top2Rec *result, cudaStream_t s) {
+  if (nq <= 0) return cudaSuccess;
+  static const int variant = [] { const char *e = getenv("ORBGPU_HAMMING_VARIANT"); return e ? atoi(e) : 1; }();
+  if (rows > 0) {
+    const int Q = hamming_dense_q(nq);
+    const int chunkRows = (rows + chunks - 1) / chunks;
+    dim3 grid(chunks, (nq + kConsumers * Q - 1) / (kConsumers * Q));
+    switch (Q) {
+      case 8: launch_dense_q<8>(variant, grid, s, bank, rows, chunkRows, indexBase, q, nq, partial); break;
+      case 4: launch_dense_q<4>(variant, grid, s, bank, rows, chunkRows, indexBase, q, nq, partial); break;
+      case 2: launch_dense_q<2>(variant, grid, s, bank, rows, chunkRows, indexBase, q, nq, partial); break;
+      default: launch_dense_q<1>(variant, grid, s, bank, rows, chunkRows, indexBase, q, nq, partial); break;
+    }
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return launch_top2_merge(partial, rows > 0 ? chunks : 0, nq, result, 0.f, 0, nullptr, s);
+}
+
+cudaError_t launch_top2_merge(const Top2Rec *parts, int nparts, int nq, Top2Rec *result, float nnratio,
+                              int thLow, long long *match, cudaStream_t s) {
+  if (nq <= 0) return cudaSuccess;
+  k_top2_merge<<<(nq + 127) / 128, 128, 0, s>>>(parts, nparts, nq, result, nnratio, thLow, match);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_hamming_csr(const uint8_t *q, int nq, const uint8_t *train, const int *offsets,
+                               const int *cand, int *idx1, int *d1, int *d2, cudaStream_t s) {
+  if (nq <= 0) return cudaSuccess;
+  k_hamming_csr<<<(nq + 3) / 4, 128, 0, s>>>(q, nq, train, offsets, cand, idx1, d1, d2);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pair_distance(const uint8_t *a, const uint8_t *b, int n, int *dist, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_pair_distance<<<(n + 255) / 256, 256, 0, s>>>(a, b, n, dist);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t run_popc_microbench(int smCount, double *popcPerSec, double *lop3PerSec) {
+  unsigned *out = nullptr;
+  cudaError_t e = cudaMalloc(&out, 4);
+  if (e != cudaSuccess) return e;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  const int iters = 4096, blocks = smCount * 8;
+  double res[2] = {0, 0};
+  for (int mode = 0; mode < 2; mode++) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+      cudaEventRecord(a);
+      if (mode == 0) k_pipe_probe<0><<<blocks, 256>>>(out, iters, 12345u + rep);
+      else k_pipe_probe<1><<<blocks, 256>>>(out, iters, 12345u + rep);
+      cudaEventRecord(b);
+      e = cudaEventSynchronize(b);
+      if (e != cudaSuccess) break;
+      float ms = 0;
+      cudaEventElapsedTime(&ms, a, b);
+      if (rep > 0 && ms < best) best = ms;
+    }
+    if (e != cudaSuccess) break;
+    res[mode] = (double)blocks * 256.0 * iters * 32.0 / (best * 1e-3);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(out);
+  if (e != cudaSuccess) return e;
+  *popcPerSec = res[0];
+  *lop3PerSec = res[1];
+  return cudaGetLastError();
+}
+
+}  // namespace orbgpu

@@ -1,0 +1,142 @@
+// Internal declarations shared by the liborbgpu.so translation units (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/orbgpu.h"
+
+namespace orbgpu {
+
+constexpr int kEdge = 19;        // EDGE_THRESHOLD, ORBextractor.cc:74
+constexpr int kHalfPatch = 15;   // HALF_PATCH_SIZE, ORBextractor.cc:73
+constexpr int kPatchSize = 31;   // PATCH_SIZE, ORBextractor.cc:72
+constexpr int kMinBorder = 16;   // EDGE_THRESHOLD - 3, ORBextractor.cc:740
+constexpr int kMaxLevels = 16;
+constexpr int kMaxRoots = 16;
+
+// Device-side status word bits (OR-ed by kernels, checked on download).
+enum : unsigned {
+  kStatusCandOverflow = 1u,   // more FAST candidates than the per-level buffer holds
+  kStatusNodeOverflow = 2u,   // octree node table too small (cannot happen by construction)
+  kStatusKpOverflow = 4u,     // more keypoints than the per-image output capacity
+};
+
+// Geometry of one pyramid level; identical on host and device (passed by value in LevelTable).
+struct LevelGeom {
+  int w, h;                 // interior size, ORBextractor.cc:1044-1045
+  int pitch;                // bytes per row of the padded plane (multiple of 16)
+  int rows;                 // h + 2*kEdge
+  unsigned long long planeBytes;   // pitch * rows rounded to 256
+  unsigned long long pyrOffset;    // byte offset of this level's [batch] array in the pyramid buffer
+  // FAST cell grid, ORBextractor.cc:740-754
+  int maxBX, maxBY;         // w - 16, h - 16
+  int nCols, nRows, wCell, hCell;
+  // octree, ORBextractor.cc:535-554
+  int quota;                // mnFeaturesPerLevel
+  int nIni;
+  float hX;
+  int rootX0[kMaxRoots], rootX1[kMaxRoots];
+  int maxNodes;             // node table size for this level
+  // buffers
+  int candCap;              // candidate rows per image
+  unsigned long long candOffset;   // in uint2 units: level base in candidate buffer ([batch][candCap])
+  int selCap;               // selected rows per image (quota + 3, padded)
+  unsigned long long selOffset;    // in int4 units
+  float scale, invScale;
+  int patchSize;            // (int)(31 * scale), ORBextractor.cc:800
+  // resize tables (level >= 1): offsets into the int2 table buffer
+  int xTab, yTab;
+};
+
+struct LevelTable {
+  int nlevels;
+  int iniTh, minTh;
+  int kpCap;                // output keypoint rows per image
+  LevelGeom lv[kMaxLevels];
+};
+
+struct Cand {   // one FAST candidate / selected keypoint: octree coordinates + response
+  unsigned xy;  // x | y << 16
+  unsigned resp;
+};
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define ORBGPU_CUDA_CHECK(expr)                                                              \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      ::orbgpu::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                          __LINE__);                                                         \
+      return ORBGPU_E_CUDA;                                                                  \
+    }                                                                                        \
+  } while (0)
+
+// ---- kernel launchers (each returns a cudaError_t from the launch) ----
+struct ExtractBuffers {
+  const LevelTable *dT;     // device copy of the level table
+  uint8_t *pyr;             // all levels, [level][batch] padded planes
+  uint8_t *blur;            // same layout
+  const int2 *tabs;         // resize tables
+  Cand *cand;               // [level][batch][candCap]
+  int *candCount;           // [batch][kMaxLevels]
+  unsigned short *nodeOf;   // octree scratch, same indexing as cand
+  int4 *sel;                // [level][batch][selCap]: x_level, y_level, response, 0
+  int *selCount;            // [batch][kMaxLevels]
+  orbgpu_keypoint *kps;     // [batch][kpCap]
+  uint8_t *desc;            // [batch][kpCap][32]
+  int *kpCount;             // [batch]
+  int *levelStart;          // [batch][kMaxLevels+1] prefix of selCount
+  unsigned *status;         // one word
+};
+
+cudaError_t launch_import_level0(const LevelTable &T, const ExtractBuffers &B, const uint8_t *src,
+                                 size_t rowStep, size_t imgStep, int batch, cudaStream_t s);
+cudaError_t launch_resize_level(const LevelTable &T, const ExtractBuffers &B, int level, int batch,
+                                cudaStream_t s);
+cudaError_t launch_blur(const LevelTable &T, const ExtractBuffers &B, int batch, cudaStream_t s);
+constexpr int kFastCellsPerTile = 4;
+struct FastConfig { int imgPitch, scorePitch, scoreBytes, stageCap, smemBytes, maxTilePixels; };
+FastConfig fast_make_config(const LevelTable &T);
+cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const int4 *tiles, int ntiles,
+                        const FastConfig &c, int batch, cudaStream_t s);
+cudaError_t launch_octree(const LevelTable &T, const ExtractBuffers &B, int batch, int smemBytes,
+                          cudaStream_t s);
+int hamming_dense_q(int nq);
+cudaError_t launch_describe(const LevelTable &T, const ExtractBuffers &B, int batch, cudaStream_t s);
+size_t octree_smem_bytes(int maxNodes);
+cudaError_t octree_configure(int smemBytes);
+cudaError_t fast_configure(int smemBytes);
+
+struct StereoArgs {
+  const uint8_t *pyrL, *pyrR;
+  const orbgpu_keypoint *kpsL, *kpsR;
+  const uint8_t *descL, *descR;
+  const int *cntL, *cntR;
+  int kpCapL, kpCapR;
+  int firstL, firstR, pairs;
+  float mbf, mb;
+  float *uRight, *depth;    // [pairs][kpCapL] (indexed from 0, i.e. relative to firstL)
+  int *bestSad;             // [pairs][kpCapL]
+};
+cudaError_t launch_stereo(const LevelTable &T, const LevelTable *dT, const StereoArgs &A, int maxKp, cudaStream_t s);
+
+struct Top2Rec { int d1, d2; long long idx; };   // 16 bytes, the shard exchange unit
+static_assert(sizeof(Top2Rec) == 16, "Top2Rec must be 16 bytes");
+
+cudaError_t launch_hamming_dense(const uint8_t *bank, int rows, long long indexBase, const uint8_t *q,
+                                 int nq, Top2Rec *partial, int chunks, Top2Rec *result, cudaStream_t s);
+int hamming_dense_chunks(int rows, int nq, int smCount);
+cudaError_t launch_top2_merge(const Top2Rec *parts, int nparts, int nq, Top2Rec *result, float nnratio,
+                              int thLow, long long *match, cudaStream_t s);
+cudaError_t launch_hamming_csr(const uint8_t *q, int nq, const uint8_t *train, const int *offsets,
+                               const int *cand, int *idx1, int *d1, int *d2, cudaStream_t s);
+cudaError_t launch_pair_distance(const uint8_t *a, const uint8_t *b, int n, int *dist, cudaStream_t s);
+cudaError_t run_popc_microbench(int smCount, double *popcPerSec, double *lop3PerSec);
+
+}  // namespace orbgpu

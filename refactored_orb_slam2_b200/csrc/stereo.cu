@@ -1,0 +1,206 @@
+// Frame::ComputeStereoMatches (Frame.cc:477-646) on the device-resident outputs of two extract calls.
+//
+// k_stereo_match — one warp per LEFT keypoint:
+//   * candidate scan.  The reference buckets right keypoints by image row (vRowIndices) and scans
+//     the bucket of row (size_t)vL in ascending iR; bucket membership is
+//     floor(yR - r) <= row <= ceil(yR + r), r = 2*scale[octR] (Frame.cc:493-502).  Lanes stride over
+//     all right keypoints applying that predicate plus the octave and u-range gates
+//     (Frame.cc:540-545); each lane keeps its first minimum, a shuffle reduction on
+//     (distance, iR) lexicographic order reproduces the sequential strict-'<' scan.
+//   * 11 x 11 SAD at 11 offsets on the keypoint's pyramid level (Frame.cc:557-600): patches are
+//     centre-subtracted integers, the L1 norm is exact in int; lanes split the 121 pixels.
+//   * parabola fit, disparity and depth in the reference's float order with _rn intrinsics
+//     (Frame.cc:606-629).
+// k_stereo_filter — one CTA per pair: median of the matched SADs by a two-level (high byte, low
+//     byte) histogram select — the same value as sort()[size/2].first — then every match with
+//     SAD >= 1.5f*1.4f*median is withdrawn (Frame.cc:634-645).
+#include "internal.cuh"
+
+namespace orbgpu {
+
+namespace {
+
+constexpr int kThHigh = 100, kThLow = 50;   // ORBmatcher.cc:38-39
+
+__device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1) {
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+         __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+constexpr int kWarps = 8;
+
+__global__ void __launch_bounds__(kWarps * 32)
+k_stereo_match(const LevelTable *__restrict__ T, StereoArgs A) {
+  const int pair = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int iL = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int imgL = A.firstL + pair, imgR = A.firstR + pair;
+  const int nL = A.cntL[imgL], nR = A.cntR[imgR];
+  if (iL >= nL) return;
+  const size_t outIdx = (size_t)pair * A.kpCapL + iL;
+  const orbgpu_keypoint *kL = A.kpsL + (size_t)imgL * A.kpCapL;
+  const orbgpu_keypoint *kR = A.kpsR + (size_t)imgR * A.kpCapR;
+  const uint4 *dL = reinterpret_cast<const uint4 *>(A.descL + ((size_t)imgL * A.kpCapL + iL) * 32);
+  const uint4 *dR = reinterpret_cast<const uint4 *>(A.descR + (size_t)imgR * A.kpCapR * 32);
+
+  float uRight = -1.0f, depth = -1.0f;
+  int sadOut = -1;
+
+  const orbgpu_keypoint kp = kL[iL];
+  const int levelL = kp.octave;
+  const float vL = kp.y, uL = kp.x;
+  const int rowL = (int)vL;
+  const float minD = 0.f, maxD = __fdiv_rn(A.mbf, A.mb);
+  const float minU = __fsub_rn(uL, maxD), maxU = __fsub_rn(uL, minD);
+
+  int bestDist = kThHigh, bestR = 0x7fffffff;
+  if (!(maxU < 0)) {
+    const uint4 a0 = dL[0], a1 = dL[1];
+    for (int iR = lane; iR < nR; iR += 32) {
+      const orbgpu_keypoint kr = kR[iR];
+      const float r = __fmul_rn(2.0f, T->lv[kr.octave].scale);
+      const int maxr = (int)ceilf(__fadd_rn(kr.y, r)), minr = (int)floorf(__fsub_rn(kr.y, r));
+      if (rowL < minr || rowL > maxr) continue;
+      if (kr.octave < levelL - 1 || kr.octave > levelL + 1) continue;
+      if (!(kr.x >= minU && kr.x <= maxU)) continue;
+      const int d = hamming256(a0, a1, dR[2 * iR], dR[2 * iR + 1]);
+      if (d < bestDist) { bestDist = d; bestR = iR; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int od = __shfl_xor_sync(0xffffffffu, bestDist, o);
+    const int orr = __shfl_xor_sync(0xffffffffu, bestR, o);
+    if (od < bestDist || (od == bestDist && orr < bestR)) { bestDist = od; bestR = orr; }
+  }
+
+  if (bestDist < (kThHigh + kThLow) / 2) {
+    const LevelGeom &G = T->lv[levelL];
+    const float uR0 = kR[bestR].x;
+    const float sf = G.invScale;
+    const float suL = roundf(__fmul_rn(kp.x, sf)), svL = roundf(__fmul_rn(kp.y, sf));
+    const float suR0 = roundf(__fmul_rn(uR0, sf));
+    const int w = 5, L = 5;
+    const float iniu = suR0 + (float)(L - w), endu = suR0 + (float)(L + w + 1);
+    if (!(iniu < 0 || endu >= (float)G.w)) {
+      const int cy = (int)svL, cxL = (int)suL, cxR = (int)suR0;
+      const uint8_t *PL = A.pyrL + G.pyrOffset + (size_t)imgL * G.planeBytes + (size_t)(cy + kEdge) * G.pitch + (cxL + kEdge);
+      const uint8_t *PR = A.pyrR + G.pyrOffset + (size_t)imgR * G.planeBytes + (size_t)(cy + kEdge) * G.pitch + (cxR + kEdge);
+      const int centreL = PL[0];
+      // left patch values of this lane's pixels (4 strides over the 121 pixels)
+      int lv[4], off[4];
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int i = lane + 32 * t;
+        const int dy = i / 11 - w, dx = i % 11 - w;
+        off[t] = dy * G.pitch + dx;
+        lv[t] = i < 121 ? (int)PL[off[t]] - centreL : 0;
+      }
+      int best = 0x7fffffff, bestInc = 0;
+      float dist[11];
+#pragma unroll
+      for (int inc = -L; inc <= L; inc++) {
+        const int centreR = PR[inc];
+        int sad = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+          if (lane + 32 * t < 121) sad += abs(lv[t] - ((int)PR[off[t] + inc] - centreR));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sad += __shfl_xor_sync(0xffffffffu, sad, o);
+        dist[inc + L] = (float)sad;
+        if (sad < best) { best = sad; bestInc = inc; }
+      }
+      if (!(bestInc == -L || bestInc == L)) {
+        float d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+        for (int k = 1; k < 10; k++)
+          if (k == bestInc + L) { d1 = dist[k - 1]; d2 = dist[k]; d3 = dist[k + 1]; }
+        const float deltaR = __fdiv_rn(__fsub_rn(d1, d3),
+                                       __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
+        if (!(deltaR < -1 || deltaR > 1)) {
+          float bestuR = __fmul_rn(G.scale, __fadd_rn(__fadd_rn(suR0, (float)bestInc), deltaR));
+          float disparity = __fsub_rn(uL, bestuR);
+          if (disparity >= minD && disparity < maxD) {
+            if (disparity <= 0) {
+              disparity = (float)0.01;
+              bestuR = (float)((double)uL - 0.01);
+            }
+            depth = __fdiv_rn(A.mbf, disparity);
+            uRight = bestuR;
+            sadOut = best;
+          }
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    A.uRight[outIdx] = uRight;
+    A.depth[outIdx] = depth;
+    A.bestSad[outIdx] = sadOut;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_stereo_filter(StereoArgs A) {
+  __shared__ int sHist[256];
+  __shared__ int sBin, sRank, sCount;
+  const int pair = blockIdx.x, tid = threadIdx.x;
+  const int nL = A.cntL[A.firstL + pair];
+  const int *sad = A.bestSad + (size_t)pair * A.kpCapL;
+  float *uRight = A.uRight + (size_t)pair * A.kpCapL, *depth = A.depth + (size_t)pair * A.kpCapL;
+
+  sHist[tid] = 0;
+  if (tid == 0) sCount = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int i = tid; i < nL; i += 256) {
+    const int s = sad[i];
+    if (s >= 0) { atomicAdd(&sHist[min(s >> 8, 255)], 1); mine++; }
+  }
+  if (mine) atomicAdd(&sCount, mine);
+  __syncthreads();
+  const int count = sCount;
+  if (count == 0) return;             // reference: undefined behaviour (Frame.cc:635); nothing to filter
+  if (tid == 0) {
+    int rank = count / 2, b = 0;
+    while (rank >= sHist[b]) { rank -= sHist[b]; b++; }
+    sBin = b; sRank = rank;
+  }
+  __syncthreads();
+  const int bin = sBin;
+  __syncthreads();
+  sHist[tid] = 0;
+  __syncthreads();
+  for (int i = tid; i < nL; i += 256) {
+    const int s = sad[i];
+    if (s >= 0 && min(s >> 8, 255) == bin) atomicAdd(&sHist[s & 255], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int rank = sRank, b = 0;
+    while (rank >= sHist[b]) { rank -= sHist[b]; b++; }
+    sBin = (bin << 8) | b;
+  }
+  __syncthreads();
+  const float median = (float)sBin;
+  const float thDist = __fmul_rn(1.5f * 1.4f, median);
+  for (int i = tid; i < nL; i += 256) {
+    const int s = sad[i];
+    if (s >= 0 && !((float)s < thDist)) { uRight[i] = -1.0f; depth[i] = -1.0f; }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_stereo(const LevelTable &T, const LevelTable *dT, const StereoArgs &A, int maxKp, cudaStream_t s) {
+  dim3 grid((maxKp + kWarps - 1) / kWarps, A.pairs);
+  k_stereo_match<<<grid, kWarps * 32, 0, s>>>(dT, A);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  k_stereo_filter<<<A.pairs, 256, 0, s>>>(A);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace orbgpu

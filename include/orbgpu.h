@@ -158,7 +158,8 @@ void orbgpu_bank_destroy(orbgpu_bank *b);
 int orbgpu_hamming_top2_dense(orbgpu_bank *bank, const uint8_t *queries, int nq, int64_t *idx1,
                               int32_t *d1, int32_t *d2);
 /* Device form: d_queries [nq][32] (16-byte aligned); d_result receives nq records of
- * { int32 d1, int32 d2, int64 idx1 } (16 bytes) — the unit exchanged between bank shards. */
+ * { int32 d1, int32 d2, int64 idx1 } (16 bytes) — the unit exchanged between bank shards.
+ * `stream` is a cudaStream_t; NULL selects the bank's own (non-blocking) stream. */
 int orbgpu_hamming_top2_dense_device(orbgpu_bank *bank, const uint8_t *d_queries, int nq,
                                      void *d_result, void *stream);
 /* Merges `parts` shard results ([parts][nq] records, shard order = ascending bank index) exactly
@@ -175,6 +176,16 @@ int orbgpu_hamming_top2_csr(const uint8_t *queries, int nq, const uint8_t *train
 
 /* Measured integer-pipe peak (register-resident POPC loop): returns POPC lane-ops per second. */
 int orbgpu_measure_popc_peak(int device, double *popc_per_second, double *lop3_per_second);
+
+/* Per-stage device timing (CUDA events on the handle's stream, recorded only while enabled).
+ * Stages: 0 pyramid (import + 7 resizes), 1 FAST cells, 2 octree, 3 blur, 4 orientation+descriptor,
+ * 5 stereo (match + median filter; recorded on the LEFT handle).  orbgpu_stage_times synchronises the
+ * stream and writes each stage's mean milliseconds over the batches run since the previous call (at most
+ * the last 32; 0 for a stage that did not run), then starts a new averaging window. */
+#define ORBGPU_NUM_STAGES 6
+int orbgpu_set_profiling(orbgpu_extractor *e, int enable);
+int orbgpu_stage_times(orbgpu_extractor *e, float *milliseconds, int n);
+const char *orbgpu_stage_name(int stage);
 
 /* Kernel launches issued by this library on the calling thread since the last reset (bench's
  * gpu_launches counter). */

@@ -83,6 +83,13 @@ struct orbgpu_extractor {
   float *dURight = nullptr, *dDepth = nullptr; int *dBestSad = nullptr;
   cudaEvent_t evDone = nullptr;
   int lastBatch = 0;
+  // optional per-stage timing
+  static constexpr int kProfRing = 32;   // batches remembered between two orbgpu_stage_times calls
+  bool profiling = false;
+  cudaEvent_t evStage[kProfRing][ORBGPU_NUM_STAGES][2] = {};
+  bool stageRan[kProfRing][ORBGPU_NUM_STAGES] = {};
+  long profCount = 0;
+  int profSlot = 0;
 
   ExtractBuffers buffers() const {
     ExtractBuffers B{};
@@ -233,6 +240,14 @@ int configure(orbgpu_extractor *e, int w, int h) {
   return ORBGPU_OK;
 }
 
+struct StageTimer {
+  orbgpu_extractor *e; int stage;
+  StageTimer(orbgpu_extractor *e_, int stage_) : e(e_), stage(stage_) {
+    if (e->profiling) { cudaEventRecord(e->evStage[e->profSlot][stage][0], e->stream); e->stageRan[e->profSlot][stage] = true; }
+  }
+  ~StageTimer() { if (e->profiling) cudaEventRecord(e->evStage[e->profSlot][stage][1], e->stream); }
+};
+
 // The whole ORBextractor::operator() for `batch` device-resident images, asynchronous on e->stream.
 int run_extract(orbgpu_extractor *e, const uint8_t *dImages, int batch, int w, int h, size_t rowStep, size_t imgStep) {
   int rc = configure(e, w, h);
@@ -242,12 +257,19 @@ int run_extract(orbgpu_extractor *e, const uint8_t *dImages, int batch, int w, i
   ORBGPU_CUDA_CHECK(cudaMemsetAsync(e->dCandCount, 0, sizeof(int) * kMaxLevels * batch, s));
   ORBGPU_CUDA_CHECK(cudaMemsetAsync(e->dSelCount, 0, sizeof(int) * kMaxLevels * batch, s));
   ORBGPU_CUDA_CHECK(cudaMemsetAsync(e->dStatus, 0, sizeof(unsigned), s));
-  ORBGPU_CUDA_CHECK(launch_import_level0(e->T, B, dImages, rowStep, imgStep, batch, s));
-  for (int l = 1; l < e->T.nlevels; l++) ORBGPU_CUDA_CHECK(launch_resize_level(e->T, B, l, batch, s));
-  ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->dTiles, e->ntiles, e->fastCfg, batch, s));
-  ORBGPU_CUDA_CHECK(launch_octree(e->T, B, batch, e->octSmem, s));
-  ORBGPU_CUDA_CHECK(launch_blur(e->T, B, batch, s));
-  ORBGPU_CUDA_CHECK(launch_describe(e->T, B, batch, s));
+  if (e->profiling) {
+    e->profSlot = (int)(e->profCount++ % orbgpu_extractor::kProfRing);
+    for (bool &r : e->stageRan[e->profSlot]) r = false;
+  }
+  {
+    StageTimer t(e, 0);
+    ORBGPU_CUDA_CHECK(launch_import_level0(e->T, B, dImages, rowStep, imgStep, batch, s));
+    for (int l = 1; l < e->T.nlevels; l++) ORBGPU_CUDA_CHECK(launch_resize_level(e->T, B, l, batch, s));
+  }
+  { StageTimer t(e, 1); ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->dTiles, e->ntiles, e->fastCfg, batch, s)); }
+  { StageTimer t(e, 2); ORBGPU_CUDA_CHECK(launch_octree(e->T, B, batch, e->octSmem, s)); }
+  { StageTimer t(e, 3); ORBGPU_CUDA_CHECK(launch_blur(e->T, B, batch, s)); }
+  { StageTimer t(e, 4); ORBGPU_CUDA_CHECK(launch_describe(e->T, B, batch, s)); }
   e->lastBatch = batch;
   return ORBGPU_OK;
 }
@@ -372,6 +394,7 @@ void orbgpu_extractor_destroy(orbgpu_extractor *e) {
                   e->dSelCount, e->dKpCount, e->dKps, e->dDesc, e->dStatus, e->dURight, e->dDepth, e->dBestSad};
   for (void *q : ptrs) if (q) cudaFree(q);
   if (e->evDone) cudaEventDestroy(e->evDone);
+  for (auto &slot : e->evStage) for (auto &p : slot) for (cudaEvent_t ev : p) if (ev) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -387,6 +410,44 @@ int orbgpu_extractor_tables(const orbgpu_extractor *e, float *scale, float *inv_
     if (features_per_level) features_per_level[i] = e->quota[i];
   }
   return ORBGPU_OK;
+}
+
+int orbgpu_set_profiling(orbgpu_extractor *e, int enable) {
+  if (!e) { set_error("null handle"); return ORBGPU_E_INVALID; }
+  DeviceGuard guard(e->device);
+  if (enable && !e->evStage[0][0][0])
+    for (auto &slot : e->evStage) for (auto &p : slot) for (cudaEvent_t &ev : p) ORBGPU_CUDA_CHECK(cudaEventCreate(&ev));
+  e->profiling = enable != 0;
+  e->profCount = 0;
+  return ORBGPU_OK;
+}
+
+int orbgpu_stage_times(orbgpu_extractor *e, float *milliseconds, int n) {
+  if (!e || !milliseconds) { set_error("null argument"); return ORBGPU_E_INVALID; }
+  DeviceGuard guard(e->device);
+  ORBGPU_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  const int slots = (int)std::min<long>(e->profCount, orbgpu_extractor::kProfRing);
+  for (int i = 0; i < n; i++) {
+    milliseconds[i] = 0.f;
+    if (i >= ORBGPU_NUM_STAGES || !e->profiling) continue;
+    double sum = 0;
+    int cnt = 0;
+    for (int k = 0; k < slots; k++) {
+      if (!e->stageRan[k][i]) continue;
+      float ms = 0.f;
+      ORBGPU_CUDA_CHECK(cudaEventElapsedTime(&ms, e->evStage[k][i][0], e->evStage[k][i][1]));
+      sum += ms; cnt++;
+    }
+    if (cnt) milliseconds[i] = (float)(sum / cnt);
+  }
+  e->profCount = 0;   // the next batch starts a new averaging window
+  for (auto &slot : e->stageRan) for (bool &r : slot) r = false;
+  return ORBGPU_OK;
+}
+
+const char *orbgpu_stage_name(int stage) {
+  static const char *names[ORBGPU_NUM_STAGES] = {"pyramid", "fast", "octree", "blur", "describe", "stereo"};
+  return stage >= 0 && stage < ORBGPU_NUM_STAGES ? names[stage] : "";
 }
 
 int orbgpu_extractor_capacity(const orbgpu_extractor *e) { return e ? e->kpCap : ORBGPU_E_INVALID; }
@@ -572,7 +633,7 @@ int orbgpu_stereo_match_device(orbgpu_extractor *L, orbgpu_extractor *R, int fir
   A.cntL = L->dKpCount; A.cntR = R->dKpCount; A.kpCapL = L->kpCap; A.kpCapR = R->kpCap;
   A.firstL = first_left; A.firstR = first_right; A.pairs = pairs; A.mbf = mbf; A.mb = mb;
   A.uRight = L->dURight; A.depth = L->dDepth; A.bestSad = L->dBestSad;
-  ORBGPU_CUDA_CHECK(launch_stereo(L->T, L->dT, A, L->kpCap, L->stream));
+  { StageTimer t(L, 5); ORBGPU_CUDA_CHECK(launch_stereo(L->T, L->dT, A, L->kpCap, L->stream)); }
   if (R != L) {   // the right handle must not overwrite its buffers before the match has read them
     ORBGPU_CUDA_CHECK(cudaEventRecord(L->evDone, L->stream));
     ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(R->stream, L->evDone, 0));

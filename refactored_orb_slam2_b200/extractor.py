@@ -163,6 +163,15 @@ class ORBextractor:
     def synchronize(self):
         check(lib().orbgpu_synchronize(self._h))
 
+    def set_profiling(self, enable=True):
+        check(lib().orbgpu_set_profiling(self._h, int(enable)))
+
+    def stage_times(self):
+        """{stage name: milliseconds} of the last batch (needs set_profiling(True)); synchronises."""
+        ms = np.zeros(6, np.float32)
+        check(lib().orbgpu_stage_times(self._h, ptr(ms), 6))
+        return {lib().orbgpu_stage_name(i).decode(): float(ms[i]) for i in range(6)}
+
     @property
     def stream(self):
         return lib().orbgpu_extractor_stream(self._h)

@@ -1,0 +1,67 @@
+"""Frame::ComputeStereoMatches parity: mvuRight / mvDepth bit-exact against the oracle (north_star
+allows 1e-3 px; the float sequence is reproduced exactly, so the tolerance is 0)."""
+import numpy as np
+import pytest
+
+import gen_synth
+import oracle
+
+pytestmark = pytest.mark.gpu
+KITTI = (386.1448, 718.856)      # bf, fx: Examples/Stereo/KITTI00-02.yaml:8,25
+EUROC = (47.90639384423901, 435.2046959714599)   # Examples/Stereo/EuRoC.yaml:8,25
+
+
+@pytest.fixture(scope="module")
+def pkg(built):
+    import refactored_orb_slam2_b200 as p
+    return p
+
+
+def oracle_pair(params, left, right, bf, fx):
+    ol, orr = oracle.OracleExtractor(*params), oracle.OracleExtractor(*params)
+    kl, dl = ol(left)
+    kr, dr = orr(right)
+    u, z, sad, kept = oracle.stereo(ol, orr, kl, dl, kr, dr, bf, np.float32(np.float32(bf) / np.float32(fx)))
+    return len(kl), u, z, kept
+
+
+@pytest.mark.parametrize("w,h,nf,cam,seed", [(1241, 376, 2000, KITTI, 2), (752, 480, 1200, EUROC, 1000), (640, 480, 1000, KITTI, 5)])
+def test_stereo_pair_parity(pkg, w, h, nf, cam, seed):
+    left, right = gen_synth.stereo_pair(h, w, seed)
+    params = (nf, 1.2, 8, 20, 7)
+    bf, fx = cam
+    n, ou, oz, kept = oracle_pair(params, left, right, bf, fx)
+    f = pkg.Frame(left, right, pkg.ORBextractor(*params), pkg.ORBextractor(*params), bf, fx)
+    assert f.N == n
+    assert np.array_equal(f.mvuRight, ou)
+    assert np.array_equal(f.mvDepth, oz)
+    assert kept > n // 4, "the synthetic pair should yield plenty of stereo matches"
+    assert int((f.mvuRight >= 0).sum()) == kept
+
+
+def test_batched_pairs_one_handle(pkg):
+    """EuRoC-shaped pairs batched on one handle: left images first, right images after them."""
+    npairs = 5
+    left, right = gen_synth.frame_batch(npairs, 480, 752, 1000, stereo=True)
+    params = (1200, 1.2, 8, 20, 7)
+    bf, fx = EUROC
+    g = pkg.ORBextractor(*params, max_width=752, max_height=480, max_batch=2 * npairs)
+    kps, desc, counts = g.extract_batch(np.concatenate([left, right]))
+    u, z = pkg.ComputeStereoMatches(g, g, bf, np.float32(bf) / np.float32(fx), first_left=0, first_right=npairs, pairs=npairs)
+    for i in range(npairs):
+        n, ou, oz, kept = oracle_pair(params, left[i], right[i], bf, fx)
+        assert counts[i] == n
+        assert np.array_equal(u[i, :n], ou) and np.array_equal(z[i, :n], oz), "pair %d" % i
+
+
+def test_integer_shift_recovers_disparity(pkg):
+    """Size-independent property: right = left shifted by d px  =>  uL - uR ~= d for the matches."""
+    d = 23
+    canvas = gen_synth.texture(376, 1241 + d, 9)
+    left, right = np.ascontiguousarray(canvas[:, d:]), np.ascontiguousarray(canvas[:, :-d])
+    f = pkg.Frame(left, right, pkg.ORBextractor(2000, 1.2, 8, 20, 7), pkg.ORBextractor(2000, 1.2, 8, 20, 7), *KITTI)
+    m = f.mvuRight >= 0
+    assert m.sum() > 500
+    disp = f.mvKeys["x"][m] - f.mvuRight[m]
+    assert abs(np.median(disp) + d) < 0.5 or abs(np.median(disp) - d) < 0.5
+    assert np.allclose(f.mvDepth[m], np.float32(KITTI[0]) / disp, rtol=1e-6)

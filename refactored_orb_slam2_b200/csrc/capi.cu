@@ -8,6 +8,7 @@
 #include <mutex>
 
 #include "internal.cuh"
+#include "tma.cuh"
 
 namespace orbgpu {
 
@@ -68,6 +69,10 @@ struct orbgpu_extractor {
   int2 *dTabs = nullptr; size_t tabsCap = 0;
   int4 *dTiles = nullptr; size_t tilesCap = 0; int ntiles = 0;
   FastConfig fastCfg{};
+  TmaMaps fastMaps{}, blurMaps{}, rzMaps{};
+  int4 *dRzTiles = nullptr; size_t rzTilesCap = 0; int rzTileOff[kMaxLevels] = {}, rzTileCnt[kMaxLevels] = {};
+  int rzSlotBytes = 0;
+  int4 *dBlurTiles = nullptr; size_t blurTilesCap = 0; int nBlurTiles = 0;
   int octSmem = 0;
 
   // buffers (sized for max_width x max_height x max_batch)
@@ -161,6 +166,12 @@ int build_table(const orbgpu_extractor &e, int w, int h, int batchCap, LevelTabl
     selOff += (size_t)G.selCap * batchCap;
     G.scale = e.scale[l]; G.invScale = e.invScale[l];
     G.patchSize = (int)(kPatchSize * e.scale[l]);                     // ORBextractor.cc:800
+    G.fastBoxW = (int)round_up(12 + 4 + kFastCellsPerTile * G.wCell + 3 + 8, 16);   // lead + left word + tile + overhang + right words
+    G.fastBoxH = G.hCell + 6;
+    if (l > 0) {
+      resize_box(T, l, &G.rzBoxW, &G.rzBoxH);
+      if (G.rzBoxW > 256 || G.rzBoxH > 256) G.rzBoxW = G.rzBoxH = 0;   // large scale factors: generic kernel
+    }
     if (l > 0) {
       const LevelGeom &P = T.lv[l - 1];
       G.xTab = (int)tabs.size(); tabs.resize(tabs.size() + G.w);
@@ -204,9 +215,16 @@ int configure(orbgpu_extractor *e, int w, int h) {
     set_error("nfeatures too large for the shared-memory octree (%d nodes, %d bytes)", maxNodes, octSmem);
     return ORBGPU_E_UNSUPPORTED;
   }
-  if (fc.maxTilePixels > 64 * 256) {
-    set_error("internal: FAST tile of %d pixels exceeds the 64-iteration survivor mask", fc.maxTilePixels);
+  if (fc.scorePitch > 256) {
+    set_error("internal: FAST tile of %d columns does not fit the 8-bit queue coordinates", fc.scorePitch);
     return ORBGPU_E_UNSUPPORTED;
+  }
+  TmaMaps fastMaps;
+  for (int l = 0; l < T.nlevels; l++) {
+    const LevelGeom &G = T.lv[l];
+    if (G.fastBoxW > 256 || G.fastBoxH > 256) { set_error("internal: FAST TMA box %dx%d too large", G.fastBoxW, G.fastBoxH); return ORBGPU_E_UNSUPPORTED; }
+    ORBGPU_CUDA_CHECK(encode_plane_map(&fastMaps.m[l], e->dPyr + G.pyrOffset, G.pitch, G.rows, G.planeBytes, e->p.max_batch,
+                                       G.fastBoxW, G.fastBoxH));
   }
   ORBGPU_CUDA_CHECK(cudaStreamSynchronize(e->stream));
   if (tabs.size() > e->tabsCap) {
@@ -214,6 +232,43 @@ int configure(orbgpu_extractor *e, int w, int h) {
     e->tabsCap = tabs.size() + 1024;
     ORBGPU_CUDA_CHECK(cudaMalloc(&e->dTabs, e->tabsCap * sizeof(int2)));
   }
+  std::vector<int4> rzTiles, one;
+  int rzOff[kMaxLevels] = {}, rzCnt[kMaxLevels] = {};
+  TmaMaps rzMaps;
+  for (int l = 1; l < T.nlevels; l++) {
+    const LevelGeom &G = T.lv[l], &P = T.lv[l - 1];
+    if (!G.rzBoxW) continue;
+    resize_make_tiles(T, l, one);
+    rzOff[l] = (int)rzTiles.size(); rzCnt[l] = (int)one.size();
+    rzTiles.insert(rzTiles.end(), one.begin(), one.end());
+    ORBGPU_CUDA_CHECK(encode_plane_map(&rzMaps.m[l - 1], e->dPyr + P.pyrOffset, P.pitch, P.rows, P.planeBytes, e->p.max_batch,
+                                       G.rzBoxW, G.rzBoxH));
+  }
+  const int rzSlot = resize_smem_bytes(T);
+  if (!rzTiles.empty()) {
+    if (rzTiles.size() > e->rzTilesCap) {
+      if (e->dRzTiles) cudaFree(e->dRzTiles);
+      e->rzTilesCap = rzTiles.size() + 64;
+      ORBGPU_CUDA_CHECK(cudaMalloc(&e->dRzTiles, e->rzTilesCap * sizeof(int4)));
+    }
+    ORBGPU_CUDA_CHECK(cudaMemcpyAsync(e->dRzTiles, rzTiles.data(), rzTiles.size() * sizeof(int4), cudaMemcpyHostToDevice, e->stream));
+    ORBGPU_CUDA_CHECK(resize_configure(rzSlot));
+  }
+  std::vector<int4> blurTiles;
+  blur_make_tiles(T, blurTiles);
+  TmaMaps blurMaps;
+  for (int l = 0; l < T.nlevels; l++) {
+    const LevelGeom &G = T.lv[l];
+    ORBGPU_CUDA_CHECK(encode_plane_map(&blurMaps.m[l], e->dPyr + G.pyrOffset, G.pitch, G.rows, G.planeBytes, e->p.max_batch,
+                                       blur_box_w(), blur_box_h()));
+  }
+  if (blurTiles.size() > e->blurTilesCap) {
+    if (e->dBlurTiles) cudaFree(e->dBlurTiles);
+    e->blurTilesCap = blurTiles.size() + 64;
+    ORBGPU_CUDA_CHECK(cudaMalloc(&e->dBlurTiles, e->blurTilesCap * sizeof(int4)));
+  }
+  ORBGPU_CUDA_CHECK(cudaMemcpyAsync(e->dBlurTiles, blurTiles.data(), blurTiles.size() * sizeof(int4), cudaMemcpyHostToDevice, e->stream));
+  ORBGPU_CUDA_CHECK(blur_configure());
   if (tiles.size() > e->tilesCap) {
     if (e->dTiles) cudaFree(e->dTiles);
     e->tilesCap = tiles.size() + 256;
@@ -235,7 +290,10 @@ int configure(orbgpu_extractor *e, int w, int h) {
     ORBGPU_CUDA_CHECK(octree_configure(octMax[d]));
     ORBGPU_CUDA_CHECK(fast_configure(fastMax[d]));
   }
-  e->T = T; e->ntiles = (int)tiles.size(); e->fastCfg = fc; e->octSmem = octSmem;
+  e->T = T; e->ntiles = (int)tiles.size(); e->fastCfg = fc; e->fastMaps = fastMaps; e->octSmem = octSmem;
+  e->blurMaps = blurMaps; e->nBlurTiles = (int)blurTiles.size();
+  e->rzMaps = rzMaps; e->rzSlotBytes = rzSlot;
+  for (int l = 0; l < kMaxLevels; l++) { e->rzTileOff[l] = rzOff[l]; e->rzTileCnt[l] = rzCnt[l]; }
   e->cfgW = w; e->cfgH = h;
   return ORBGPU_OK;
 }
@@ -264,11 +322,17 @@ int run_extract(orbgpu_extractor *e, const uint8_t *dImages, int batch, int w, i
   {
     StageTimer t(e, 0);
     ORBGPU_CUDA_CHECK(launch_import_level0(e->T, B, dImages, rowStep, imgStep, batch, s));
-    for (int l = 1; l < e->T.nlevels; l++) ORBGPU_CUDA_CHECK(launch_resize_level(e->T, B, l, batch, s));
+    for (int l = 1; l < e->T.nlevels; l++) {
+      if (e->T.lv[l].rzBoxW)
+        ORBGPU_CUDA_CHECK(launch_resize_tiles(e->T, B, e->rzMaps, e->dRzTiles + e->rzTileOff[l], e->rzTileCnt[l], e->rzSlotBytes, batch, s));
+      else
+        ORBGPU_CUDA_CHECK(launch_resize_level(e->T, B, l, batch, s));
+    }
+    ORBGPU_CUDA_CHECK(launch_fill_borders(e->T, B, 1, batch, s));
   }
-  { StageTimer t(e, 1); ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->dTiles, e->ntiles, e->fastCfg, batch, s)); }
+  { StageTimer t(e, 1); ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->fastMaps, e->dTiles, e->ntiles, e->fastCfg, batch, s)); }
   { StageTimer t(e, 2); ORBGPU_CUDA_CHECK(launch_octree(e->T, B, batch, e->octSmem, s)); }
-  { StageTimer t(e, 3); ORBGPU_CUDA_CHECK(launch_blur(e->T, B, batch, s)); }
+  { StageTimer t(e, 3); ORBGPU_CUDA_CHECK(launch_blur(e->T, B, e->blurMaps, e->dBlurTiles, e->nBlurTiles, batch, s)); }
   { StageTimer t(e, 4); ORBGPU_CUDA_CHECK(launch_describe(e->T, B, batch, s)); }
   e->lastBatch = batch;
   return ORBGPU_OK;
@@ -390,7 +454,7 @@ void orbgpu_extractor_destroy(orbgpu_extractor *e) {
   if (!e) return;
   DeviceGuard guard(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  void *ptrs[] = {e->dT, e->dTabs, e->dTiles, e->dInput, e->dPyr, e->dBlur, e->dCand, e->dNodeOf, e->dSel, e->dCandCount,
+  void *ptrs[] = {e->dT, e->dTabs, e->dTiles, e->dBlurTiles, e->dRzTiles, e->dInput, e->dPyr, e->dBlur, e->dCand, e->dNodeOf, e->dSel, e->dCandCount,
                   e->dSelCount, e->dKpCount, e->dKps, e->dDesc, e->dStatus, e->dURight, e->dDepth, e->dBestSad};
   for (void *q : ptrs) if (q) cudaFree(q);
   if (e->evDone) cudaEventDestroy(e->evDone);

@@ -11,71 +11,57 @@
 //   rectangle (cv::FAST scores pixels outside the rectangle, and non-corners, as 0).
 //   t = iniThFAST if the cell has at least one survivor at iniThFAST, else minThFAST.
 //
-// One CTA = up to kCellsPerTile horizontally adjacent cells of one cell row of one level of one
-// image.  The source window (+3 px ring apron) is staged in shared memory; arc margins are
-// evaluated for two horizontally adjacent pixels at a time in packed s16x2 registers with the
-// 3-input VIMNMX3.S16x2 min/max of sm_100a (a sliding min3-of-min3 gives every 9-arc in 32 ops);
-// a cheap upper bound from the 8 opposite ring pairs rejects most pixel pairs first.  Scores go to
-// a shared u8 tile, NMS + the per-cell threshold fallback run on that tile, survivors are staged in
-// shared memory and appended to the level's candidate list with one global atomic per CTA.
+// One CTA = up to kFastCellsPerTile horizontally adjacent cells of one cell row of one level of one
+// image.  The source window (+3 px ring apron) is brought into shared memory by ONE TMA tensor copy
+// (cp.async.bulk.tensor.3d on the level's [batch][rows][pitch] u8 tensor map, completion on an
+// mbarrier).  TMA needs the window's first column on a 16-byte boundary, so pixels are grouped by
+// fours on the PADDED plane's 4-byte grid (groups sit on 32-bit words in shared memory) and the up
+// to 3 + 3 pixels a row of groups overhangs the tile are masked out.  A thread owns 4 horizontally adjacent pixels: 21 LDS.32 fetch the 7 ring rows, PRMT
+// unpacks byte pairs into packed s16x2, and the arc margins of two pixels at a time come from the
+// 3-input VIMNMX3.S16x2 min/max of sm_100a (sliding min3-of-min3 = every 9-arc in 32 ops, 82 ops
+// per pixel pair for both polarities).  Scores (margin - minTh, 0 = not a corner at minTh) go to a
+// shared u8 tile and the coordinates of the non-zero ones to a shared queue (warp-aggregated
+// reservation); NMS and the per-cell threshold fallback run over that queue only; survivors are
+// staged in shared memory and appended to the level's candidate list with one global atomic per CTA.
 // Candidate order in HBM is arbitrary: the octree only needs each candidate's position in the
 // reference's cell-major order to break response ties, and that is a function of (x, y).
 #include "internal.cuh"
+#include "tma.cuh"
 
 namespace orbgpu {
 
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
 
-__device__ __forceinline__ unsigned pack2(unsigned lo, unsigned hi) { return lo | (hi << 16); }
 __device__ __forceinline__ unsigned mn3(unsigned a, unsigned b, unsigned c) { return __vimin3_s16x2(a, b, c); }
 __device__ __forceinline__ unsigned mx3(unsigned a, unsigned b, unsigned c) { return __vimax3_s16x2(a, b, c); }
-__device__ __forceinline__ unsigned mn2(unsigned a, unsigned b) { return __vmins2(a, b); }
 __device__ __forceinline__ unsigned mx2(unsigned a, unsigned b) { return __vmaxs2(a, b); }
 
-// Arc margins of the two pixels at p[0], p[1] (row pitch `sp`), packed s16x2; returns 0x80008000-ish
-// negative halves when the pair cannot reach `minTh` (prefilter), exact margins otherwise.
-__device__ __forceinline__ unsigned fast_margin_pair(const uint8_t *p, int sp, int minTh) {
+// Bytes O, O+1 of the 12-byte window (w0, w1, w2), zero-extended into packed 16x2.
+template <int O>
+__device__ __forceinline__ unsigned pair_at(unsigned w0, unsigned w1, unsigned w2) {
+  static_assert(O >= 0 && O <= 10, "window offset");
+  if constexpr (O <= 2) return __byte_perm(w0, 0u, 0x4040u | O | ((O + 1) << 8));
+  else if constexpr (O == 3) return __byte_perm(w0, w1, 0x4443u) & 0x00ff00ffu;
+  else if constexpr (O <= 6) return __byte_perm(w1, 0u, 0x4040u | (O - 4) | ((O - 3) << 8));
+  else if constexpr (O == 7) return __byte_perm(w1, w2, 0x4443u) & 0x00ff00ffu;
+  else return __byte_perm(w2, 0u, 0x4040u | (O - 8) | ((O - 7) << 8));
+}
+
+// Arc margins (packed s16x2) of the two pixels at window bytes C, C+1; rows[r] = window words of image row y-3+r.
+template <int C>
+__device__ __forceinline__ unsigned margin_pair(const unsigned (&w)[7][3]) {
+  const unsigned negc = __vneg2(pair_at<C>(w[3][0], w[3][1], w[3][2]));
   unsigned d[16];
-  {
-    const uint8_t *r;
-    const unsigned negc = __vneg2(pack2(p[0], p[1]));
-    r = p + 3 * sp;
-    { unsigned a = r[-1], b = r[0], c = r[1], e = r[2];
-      d[15] = __vadd2(pack2(a, b), negc); d[0] = __vadd2(pack2(b, c), negc); d[1] = __vadd2(pack2(c, e), negc); }
-    r = p + 2 * sp;
-    { unsigned a = r[-2], b = r[-1], c = r[2], e = r[3];
-      d[14] = __vadd2(pack2(a, b), negc); d[2] = __vadd2(pack2(c, e), negc); }
-    r = p + sp;
-    { unsigned a = r[-3], b = r[-2], c = r[3], e = r[4];
-      d[13] = __vadd2(pack2(a, b), negc); d[3] = __vadd2(pack2(c, e), negc); }
-    r = p;
-    { unsigned a = r[-3], b = r[-2], c = r[3], e = r[4];
-      d[12] = __vadd2(pack2(a, b), negc); d[4] = __vadd2(pack2(c, e), negc); }
-    r = p - sp;
-    { unsigned a = r[-3], b = r[-2], c = r[3], e = r[4];
-      d[11] = __vadd2(pack2(a, b), negc); d[5] = __vadd2(pack2(c, e), negc); }
-    r = p - 2 * sp;
-    { unsigned a = r[-2], b = r[-1], c = r[2], e = r[3];
-      d[10] = __vadd2(pack2(a, b), negc); d[6] = __vadd2(pack2(c, e), negc); }
-    r = p - 3 * sp;
-    { unsigned a = r[-1], b = r[0], c = r[1], e = r[2];
-      d[9] = __vadd2(pack2(a, b), negc); d[8] = __vadd2(pack2(b, c), negc); d[7] = __vadd2(pack2(c, e), negc); }
-  }
-  // Prefilter: every 9-arc contains one pixel of each opposite pair (k, k+8), so
-  //   bright margin <= min_k max(d_k, d_k+8)   and   dark margin <= -max_k min(d_k, d_k+8).
-  {
-    unsigned hi[8], lo[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) { hi[k] = mx2(d[k], d[k + 8]); lo[k] = mn2(d[k], d[k + 8]); }
-    const unsigned ubB = mn3(mn3(hi[0], hi[1], hi[2]), mn3(hi[3], hi[4], hi[5]), mn2(hi[6], hi[7]));
-    const unsigned lbD = mx3(mx3(lo[0], lo[1], lo[2]), mx3(lo[3], lo[4], lo[5]), mx2(lo[6], lo[7]));
-    const unsigned ub = mx2(ubB, __vneg2(lbD));
-    const int u0 = (short)(ub & 0xffff), u1 = (short)(ub >> 16);
-    if (max(u0, u1) <= minTh) return 0x80008000u;   // both halves = -32768
-  }
-  // min / max over every window of 3, then of 9 = three windows of 3 spaced by 3
+  // ring order of cv::FAST 9/16: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+#define RING(k, dx, dy) d[k] = __vadd2(pair_at<C + (dx)>(w[3 + (dy)][0], w[3 + (dy)][1], w[3 + (dy)][2]), negc)
+  RING(0, 0, 3);   RING(1, 1, 3);   RING(2, 2, 2);    RING(3, 3, 1);
+  RING(4, 3, 0);   RING(5, 3, -1);  RING(6, 2, -2);   RING(7, 1, -3);
+  RING(8, 0, -3);  RING(9, -1, -3); RING(10, -2, -2); RING(11, -3, -1);
+  RING(12, -3, 0); RING(13, -3, 1); RING(14, -2, 2);  RING(15, -1, 3);
+#undef RING
   unsigned a3[16], b3[16];
 #pragma unroll
   for (int k = 0; k < 16; k++) {
@@ -97,19 +83,19 @@ __device__ __forceinline__ unsigned fast_margin_pair(const uint8_t *p, int sp, i
 
 // tiles[t] = (level, cell row i, first cell column j0, cell count)
 __global__ void __launch_bounds__(kThreads)
-k_fast_cells(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, const int4 *__restrict__ tiles,
-             Cand *__restrict__ cand, int *__restrict__ candCount, unsigned *__restrict__ status,
-             int imgPitchMax, int scorePitchMax, int scoreBytes, int stageCap) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ int sCellCnt[8];
-  __shared__ int sEmit, sBase;
+k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict__ T, const int4 *__restrict__ tiles,
+             Cand *__restrict__ cand, int *__restrict__ candCount, unsigned *__restrict__ status, const FastConfig cfg) {
+  extern __shared__ uint8_t smemRaw[];
+  __shared__ __align__(8) unsigned long long sBar;
+  __shared__ int sCellCnt[kFastCellsPerTile];
+  __shared__ int sEmit, sBase, sQueued, sKept, sOut;
 
   const int4 tile = tiles[blockIdx.x];
   const int level = tile.x, ci = tile.y, cj0 = tile.z, nc = tile.w;
   const LevelGeom &G = T->lv[level];
   const int img = blockIdx.y;
   const int iniTh = T->iniTh, minTh = T->minTh;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   // detection rectangle of the tile, level coordinates
   const int X0 = kEdge + cj0 * G.wCell, Y0 = kEdge + ci * G.hCell;
@@ -118,95 +104,130 @@ k_fast_cells(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, 
   const int TW = X1 - X0, TH = Y1 - Y0;
   if (TW <= 0 || TH <= 0) return;
 
-  // ---- stage the source window: rows Y0-3 .. Y1+2, columns from the 4-aligned byte at or before X0-3
-  const int px0 = (X0 - 3 + kEdge) & ~3;            // padded column of staged byte 0
-  const int lead = (X0 - 3 + kEdge) - px0;          // staged column of level x = X0-3
-  const int sp = imgPitchMax;                       // staged row pitch (multiple of 4)
-  const int words = (lead + TW + 10) >> 2;           // covers the phantom pixel of an odd-width tile
-  uint8_t *sImg = smem;
-  uint8_t *sScore = smem + (size_t)sp * (G.hCell + 6);          // score tile, pitch scorePitchMax
-  Cand *sStage = reinterpret_cast<Cand *>(sScore + scoreBytes);
-  const uint8_t *S = pyr + G.pyrOffset + (size_t)img * G.planeBytes;
-  for (int i = tid; i < (TH + 6) * words; i += kThreads) {
-    const int r = i / words, c4 = i - r * words;
-    const int x = px0 + 4 * c4;
-    unsigned v = 0;
-    if (x + 3 < G.pitch) v = *reinterpret_cast<const unsigned *>(S + (size_t)(Y0 - 3 + r + kEdge) * G.pitch + x);
-    *reinterpret_cast<unsigned *>(sImg + r * sp + 4 * c4) = v;
-  }
-  if (tid < 8) sCellCnt[tid] = 0;
-  if (tid == 0) sEmit = 0;
-  __syncthreads();
+  uint8_t *smem = smemRaw + ((128u - (smem_u32(smemRaw) & 127u)) & 127u);   // TMA destination: 128-byte aligned
+  uint8_t *sImg = smem;                                   // fastBoxW x fastBoxH window
+  uint8_t *sScore = smem + cfg.imgBytes;                  // u8 scores, pitch cfg.scorePitch, column 0 = padded column gx0
+  Cand *sStage = reinterpret_cast<Cand *>(sScore + cfg.scoreBytes);
+  unsigned short *sQueue = reinterpret_cast<unsigned short *>(sStage + cfg.stageCap);   // (row << 8 | column) of non-zero scores
+  const int bw = G.fastBoxW, sp = cfg.scorePitch;
+  // 4-pixel groups on the padded plane's 4-byte grid
+  const int gx0 = (X0 + kEdge) & ~3;                      // padded column of the first group
+  const int offL = (X0 + kEdge) - gx0;                    // tile x = score column - offL
+  const int groups = (offL + TW + 3) >> 2;
+  const int bx = (gx0 - 4) & ~15;                         // window origin: 16-byte aligned for TMA
+  const int lead = (gx0 - 4) - bx;                        // 0, 4, 8 or 12
 
-  // ---- arc margins, two pixels per step
-  const int pairsPerRow = (TW + 1) >> 1;
-  for (int i = tid; i < pairsPerRow * TH; i += kThreads) {
-    const int y = i / pairsPerRow, x = (i - y * pairsPerRow) * 2;
-    const uint8_t *p = sImg + (y + 3) * sp + lead + 3 + x;
-    const unsigned m = fast_margin_pair(p, sp, minTh);
-    const int m0 = (short)(m & 0xffff), m1 = (short)(m >> 16);
-    sScore[y * scorePitchMax + x] = (uint8_t)(m0 > minTh ? m0 : 0);
-    if (x + 1 < TW) sScore[y * scorePitchMax + x + 1] = (uint8_t)(m1 > minTh ? m1 : 0);
+  if (tid == 0) {
+    mbar_init(&sBar, 1);
+    mbar_fence_init();
+    sEmit = 0; sQueued = 0; sKept = 0; sOut = 0;
   }
+  if (tid < kFastCellsPerTile) sCellCnt[tid] = 0;
   __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&sBar, (unsigned)(G.fastBoxW * G.fastBoxH));
+    tma_load_3d(sImg, &maps.m[level], bx, Y0 - 3 + kEdge, img, &sBar);
+  }
+  mbar_wait(&sBar, 0);
 
-  // ---- NMS inside each cell's rectangle; count survivors at iniTh per cell
-  unsigned long long surv = 0;
-  int it = 0;
-  for (int i = tid; i < TW * TH; i += kThreads, it++) {
-    const int y = i / TW, x = i - y * TW;
-    const int s = sScore[y * scorePitchMax + x];
-    if (s == 0) continue;
-    const int c = x / G.wCell;
-    const int cx0 = c * G.wCell, cx1 = min(cx0 + G.wCell, TW);
-    bool keep = true;
+  // ---- arc margins: a thread owns score columns 4g .. 4g+3 of row y; corners at minTh are queued
+  const unsigned th2 = (unsigned)minTh * 0x00010001u;
+  for (int y0 = 0; y0 < TH; y0 += kWarps) {
+    const int y = y0 + warp;
+    for (int g0 = 0; g0 < groups; g0 += 32) {
+      const int g = g0 + lane;
+      unsigned packed = 0;
+      if (y < TH && g < groups) {
+        unsigned w[7][3];
 #pragma unroll
-    for (int dy = -1; dy <= 1; dy++) {
-      const int ny = y + dy;
-      if (ny < 0 || ny >= TH) continue;
+        for (int r = 0; r < 7; r++) {
+          const unsigned *row = reinterpret_cast<const unsigned *>(sImg + (y + r) * bw + lead) + g;
+          w[r][0] = row[0]; w[r][1] = row[1]; w[r][2] = row[2];
+        }
+        // score = max(margin, minTh) - minTh: 0 when the pixel is not a corner at minTh
+        const unsigned sA = __vsub2(mx2(margin_pair<4>(w), th2), th2);
+        const unsigned sB = __vsub2(mx2(margin_pair<6>(w), th2), th2);
+        packed = __byte_perm(sA, sB, 0x6420u);
+        // pixels of the first / last group outside the tile's detection columns
+        const int lo = offL - 4 * g, hi = offL + TW - 4 * g;
+        if (lo > 0) packed &= 0xffffffffu << (8 * lo);
+        if (hi < 4) packed &= 0xffffffffu >> (8 * (4 - hi));
+        *reinterpret_cast<unsigned *>(sScore + y * sp + 4 * g) = packed;
+      }
+      // queue the non-zero scores: warp-aggregated reservation, (row << 8 | score column) entries
+      const int mine = (packed & 0xffu ? 1 : 0) + (packed & 0xff00u ? 1 : 0) + (packed & 0xff0000u ? 1 : 0) + (packed >> 24 ? 1 : 0);
+      int incl = mine;
 #pragma unroll
-      for (int dx = -1; dx <= 1; dx++) {
-        const int nx = x + dx;
-        if ((dx | dy) == 0 || nx < cx0 || nx >= cx1) continue;
-        keep = keep && s > sScore[ny * scorePitchMax + nx];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total) {
+        int base = 0;
+        if (lane == 31) base = atomicAdd(&sQueued, total);
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if ((packed >> (8 * k)) & 0xffu) sQueue[base++] = (unsigned short)((y << 8) | (4 * g + k));
       }
     }
+  }
+  __syncthreads();
+
+  // ---- NMS inside each cell's rectangle over the queue; survivors go to the stage list, cells count survivors at iniTh
+  const int iniS = iniTh - minTh;                         // score > iniS  <=>  margin > iniTh
+  const int nq = sQueued;
+  for (int i = tid; i < nq; i += kThreads) {
+    const int e = sQueue[i];
+    const int y = e >> 8, sx = e & 0xff;
+    const uint8_t *c0 = sScore + y * sp + sx;
+    const int s = c0[0];
+    const int x = sx - offL;                               // tile coordinate
+    const int c = (x >= G.wCell) + (x >= 2 * G.wCell) + (x >= 3 * G.wCell);
+    const int cx0 = c * G.wCell, cx1 = min(cx0 + G.wCell, TW);
+    const bool left = x > cx0, right = x + 1 < cx1, up = y > 0, down = y + 1 < TH;
+    bool keep = (!left || s > c0[-1]) && (!right || s > c0[1]);
+    if (up) keep = keep && s > c0[-sp] && (!left || s > c0[-sp - 1]) && (!right || s > c0[-sp + 1]);
+    if (down) keep = keep && s > c0[sp] && (!left || s > c0[sp - 1]) && (!right || s > c0[sp + 1]);
     if (keep) {
-      surv |= 1ull << it;
-      if (s > iniTh) atomicAdd(&sCellCnt[c], 1);
+      const int slot = atomicAdd(&sKept, 1);
+      if (slot < cfg.stageCap) {
+        Cand o;
+        o.xy = (unsigned)(X0 + x - kMinBorder) | ((unsigned)(Y0 + y - kMinBorder) << 16);
+        o.resp = (unsigned)(s + minTh - 1) | ((unsigned)c << 16);     // cv::FAST response = margin - 1; cell in the high half
+        sStage[slot] = o;
+      }
+      if (s > iniS) atomicAdd(&sCellCnt[c], 1);
     }
   }
   __syncthreads();
 
   // ---- emit: cells with no survivor at iniTh fall back to minTh (ORBextractor.cc:776-780)
-  it = 0;
-  for (int i = tid; i < TW * TH; i += kThreads, it++) {
-    if (!((surv >> it) & 1ull)) continue;
-    const int y = i / TW, x = i - y * TW;
-    const int s = sScore[y * scorePitchMax + x];
-    const int c = x / G.wCell;
-    if (s > iniTh || sCellCnt[c] == 0) {
-      const int slot = atomicAdd(&sEmit, 1);
-      if (slot < stageCap) {
-        Cand k;
-        k.xy = (unsigned)(X0 + x - kMinBorder) | ((unsigned)(Y0 + y - kMinBorder) << 16);
-        k.resp = (unsigned)(s - 1);
-        sStage[slot] = k;
-      }
-    }
+  const int nk = min(sKept, cfg.stageCap);
+  if (tid == 0 && sKept > cfg.stageCap) atomicOr(status, kStatusCandOverflow);
+  int myEmit = 0;
+  for (int i = tid; i < nk; i += kThreads) {
+    const Cand o = sStage[i];
+    const int s = (int)(o.resp & 0xffffu) + 1 - minTh, c = (int)(o.resp >> 16);
+    myEmit += (s > iniS || sCellCnt[c] == 0) ? 1 : 0;
   }
+  if (myEmit) atomicAdd(&sEmit, myEmit);
   __syncthreads();
-  const int n = min(sEmit, stageCap);
-  if (tid == 0) {
-    sBase = n > 0 ? atomicAdd(&candCount[img * kMaxLevels + level], n) : 0;
-    if (sEmit > stageCap) atomicOr(status, kStatusCandOverflow);
-  }
+  if (tid == 0) sBase = sEmit > 0 ? atomicAdd(&candCount[img * kMaxLevels + level], sEmit) : 0;
   __syncthreads();
   const int base = sBase;
-  if (base + n > G.candCap && tid == 0) atomicOr(status, kStatusCandOverflow);
+  if (tid == 0 && base + sEmit > G.candCap) atomicOr(status, kStatusCandOverflow);
   Cand *out = cand + G.candOffset + (size_t)img * G.candCap;
-  for (int i = tid; i < n; i += kThreads)
-    if (base + i < G.candCap) out[base + i] = sStage[i];
+  for (int i = tid; i < nk; i += kThreads) {
+    Cand o = sStage[i];
+    const int s = (int)(o.resp & 0xffffu) + 1 - minTh, c = (int)(o.resp >> 16);
+    if (s > iniS || sCellCnt[c] == 0) {
+      const int slot = base + atomicAdd(&sOut, 1);
+      o.resp &= 0xffffu;
+      if (slot < G.candCap) out[slot] = o;
+    }
+  }
 }
 
 }  // namespace
@@ -215,25 +236,29 @@ cudaError_t fast_configure(int smemBytes) {
   return cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
 }
 
+// Shared-memory budget of the FAST kernel for a level table (whose fastBoxW / fastBoxH are already set).
 FastConfig fast_make_config(const LevelTable &T) {
-  int wMax = 0, hMax = 0;
-  for (int l = 0; l < T.nlevels; l++) { wMax = max(wMax, T.lv[l].wCell); hMax = max(hMax, T.lv[l].hCell); }
+  int wMax = 0, hMax = 0, img = 0;
+  for (int l = 0; l < T.nlevels; l++) {
+    wMax = max(wMax, T.lv[l].wCell); hMax = max(hMax, T.lv[l].hCell);
+    img = max(img, T.lv[l].fastBoxW * T.lv[l].fastBoxH);
+  }
   FastConfig c;
   const int tw = kFastCellsPerTile * wMax;
-  c.imgPitch = (3 + tw + 10 + 3) & ~3;
-  c.scorePitch = (tw + 3) & ~3;
+  c.imgBytes = (img + 127) & ~127;
+  c.scorePitch = (tw + 3 + 3 + 3) & ~3;             // + the group overhang on both sides
   c.scoreBytes = (c.scorePitch * hMax + 15) & ~15;
   c.stageCap = (tw / 2 + 1) * (hMax / 2 + 1);      // bound on strict 8-neighbour maxima in a tile
-  c.smemBytes = c.imgPitch * (hMax + 6) + c.scoreBytes + c.stageCap * (int)sizeof(Cand);
-  c.maxTilePixels = tw * hMax;
+  c.queueCap = c.scorePitch * hMax;
+  c.smemBytes = 128 + c.imgBytes + c.scoreBytes + c.stageCap * (int)sizeof(Cand) + c.queueCap * 2;
+  c.maxIters = ((hMax + kWarps - 1) / kWarps) * (((tw + 6 + 3) / 4 + 31) / 32);
   return c;
 }
 
-cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const int4 *tiles, int ntiles,
+cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &maps, const int4 *tiles, int ntiles,
                         const FastConfig &c, int batch, cudaStream_t s) {
   dim3 grid(ntiles, batch);
-  k_fast_cells<<<grid, kThreads, c.smemBytes, s>>>(B.dT, B.pyr, tiles, B.cand, B.candCount, B.status, c.imgPitch,
-                                                    c.scorePitch, c.scoreBytes, c.stageCap);
+  k_fast_cells<<<grid, kThreads, c.smemBytes, s>>>(maps, B.dT, tiles, B.cand, B.candCount, B.status, c);
   count_launch();
   return cudaGetLastError();
 }

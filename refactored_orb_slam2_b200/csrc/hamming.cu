@@ -19,6 +19,7 @@
 #include <cstdlib>
 
 #include "internal.cuh"
+#include "tma.cuh"
 
 namespace orbgpu {
 
@@ -29,32 +30,6 @@ constexpr int kDenseThreads = kConsumers + 32;   // + one producer warp
 constexpr int kTileRows = 128;
 constexpr int kStages = 4;
 constexpr int kTileBytes = kTileRows * 32;
-
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 template <int IMM>
 __device__ __forceinline__ unsigned lop3(unsigned a, unsigned b, unsigned c) {
@@ -93,7 +68,7 @@ k_hamming_dense(const uint8_t *__restrict__ bank, int rows, int chunkRows, long 
 
   if (tid == 0) {
     for (int s = 0; s < kStages; s++) { mbar_init(&sFull[s], 1); mbar_init(&sEmpty[s], kConsumers / 32); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   __syncthreads();
 
@@ -162,23 +137,40 @@ k_hamming_dense(const uint8_t *__restrict__ bank, int rows, int chunkRows, long 
   }
 }
 
-// Folds `nparts` records per query in ascending part order == ascending bank index.
-__global__ void k_top2_merge(const Top2Rec *__restrict__ parts, int nparts, int nq, Top2Rec *__restrict__ result,
-                             float nnratio, int thLow, long long *__restrict__ match) {
-  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+// Folds `nparts` records per query in ascending part order == ascending bank index.  One warp per query:
+// lanes stride over the parts, then a shuffle tree folds lane results; (d1, idx) lexicographic order stands in
+// for "earlier part first" because bank indices grow with the part number.
+__device__ __forceinline__ void fold_top2(int &d1, int &d2, long long &idx, int e1, int e2, long long eidx) {
+  if (e1 < d1 || (e1 == d1 && eidx >= 0 && (idx < 0 || eidx < idx))) { d2 = min(d1, e2); d1 = e1; idx = eidx; }
+  else d2 = min(d2, e1);
+}
+
+__global__ void __launch_bounds__(256)
+k_top2_merge(const Top2Rec *__restrict__ parts, int nparts, int nq, Top2Rec *__restrict__ result,
+             float nnratio, int thLow, long long *__restrict__ match) {
+  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (qi >= nq) return;
   int d1 = 256, d2 = 256;
   long long idx = -1;
-  for (int p = 0; p < nparts; p++) {
+  for (int p = lane; p < nparts; p += 32) {
     const Top2Rec r = parts[(size_t)p * nq + qi];
-    if (r.d1 < d1) { d2 = min(d1, r.d2); d1 = r.d1; idx = r.idx; }
-    else d2 = min(d2, r.d1);
+    fold_top2(d1, d2, idx, r.d1, r.d2, r.idx);
   }
-  if (result) { Top2Rec o; o.d1 = d1; o.d2 = d2; o.idx = idx; result[qi] = o; }
-  if (match) {
-    // ORBmatcher.cc:224-226
-    const bool ok = d1 <= thLow && (float)d1 < __fmul_rn(nnratio, (float)d2);
-    match[qi] = ok ? idx : -1ll;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int e1 = __shfl_xor_sync(0xffffffffu, d1, o);
+    const int e2 = __shfl_xor_sync(0xffffffffu, d2, o);
+    const long long eidx = __shfl_xor_sync(0xffffffffu, idx, o);
+    fold_top2(d1, d2, idx, e1, e2, eidx);
+  }
+  if (lane == 0) {
+    if (result) { Top2Rec o; o.d1 = d1; o.d2 = d2; o.idx = idx; result[qi] = o; }
+    if (match) {
+      // ORBmatcher.cc:224-226
+      const bool ok = d1 <= thLow && (float)d1 < __fmul_rn(nnratio, (float)d2);
+      match[qi] = ok ? idx : -1ll;
+    }
   }
 }
 
@@ -294,7 +286,7 @@ cudaError_t launch_hamming_dense(const uint8_t *bank, int rows, long long indexB
 cudaError_t launch_top2_merge(const Top2Rec *parts, int nparts, int nq, Top2Rec *result, float nnratio,
                               int thLow, long long *match, cudaStream_t s) {
   if (nq <= 0) return cudaSuccess;
-  k_top2_merge<<<(nq + 127) / 128, 128, 0, s>>>(parts, nparts, nq, result, nnratio, thLow, match);
+  k_top2_merge<<<(nq + 7) / 8, 256, 0, s>>>(parts, nparts, nq, result, nnratio, thLow, match);
   count_launch();
   return cudaGetLastError();
 }

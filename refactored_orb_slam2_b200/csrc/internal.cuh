@@ -50,6 +50,9 @@ struct LevelGeom {
   int patchSize;            // (int)(31 * scale), ORBextractor.cc:800
   // resize tables (level >= 1): offsets into the int2 table buffer
   int xTab, yTab;
+  // TMA boxes (bytes x rows) of the kernels that stage this level in shared memory
+  int fastBoxW, fastBoxH;
+  int rzBoxW, rzBoxH;       // source window of the tiled resize that PRODUCES this level (0 = generic kernel)
 };
 
 struct LevelTable {
@@ -77,6 +80,8 @@ void count_launch(int n = 1);
     }                                                                                        \
   } while (0)
 
+struct TmaMaps;   // tma.cuh
+
 // ---- kernel launchers (each returns a cudaError_t from the launch) ----
 struct ExtractBuffers {
   const LevelTable *dT;     // device copy of the level table
@@ -99,11 +104,24 @@ cudaError_t launch_import_level0(const LevelTable &T, const ExtractBuffers &B, c
                                  size_t rowStep, size_t imgStep, int batch, cudaStream_t s);
 cudaError_t launch_resize_level(const LevelTable &T, const ExtractBuffers &B, int level, int batch,
                                 cudaStream_t s);
-cudaError_t launch_blur(const LevelTable &T, const ExtractBuffers &B, int batch, cudaStream_t s);
+void resize_box(const LevelTable &T, int l, int *boxW, int *boxH);
+int resize_smem_bytes(const LevelTable &T);
+cudaError_t resize_configure(int slotBytes);
+void resize_make_tiles(const LevelTable &T, int level, std::vector<int4> &tiles);
+cudaError_t launch_resize_tiles(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &maps, const int4 *tiles,
+                                int ntiles, int slotBytes, int batch, cudaStream_t s);
+cudaError_t launch_fill_borders(const LevelTable &T, const ExtractBuffers &B, int firstLevel, int batch, cudaStream_t s);
+cudaError_t launch_blur(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &maps, const int4 *tiles, int ntiles,
+                        int batch, cudaStream_t s);
+int blur_box_w();
+int blur_box_h();
+int blur_smem_bytes();
+cudaError_t blur_configure();
+void blur_make_tiles(const LevelTable &T, std::vector<int4> &tiles);
 constexpr int kFastCellsPerTile = 4;
-struct FastConfig { int imgPitch, scorePitch, scoreBytes, stageCap, smemBytes, maxTilePixels; };
+struct FastConfig { int imgBytes, scorePitch, scoreBytes, stageCap, queueCap, smemBytes, maxIters; };
 FastConfig fast_make_config(const LevelTable &T);
-cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const int4 *tiles, int ntiles,
+cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &maps, const int4 *tiles, int ntiles,
                         const FastConfig &c, int batch, cudaStream_t s);
 cudaError_t launch_octree(const LevelTable &T, const ExtractBuffers &B, int batch, int smemBytes,
                           cudaStream_t s);

@@ -176,6 +176,9 @@ int orbgpu_hamming_top2_csr(const uint8_t *queries, int nq, const uint8_t *train
 
 /* Measured integer-pipe peak (register-resident POPC loop): returns POPC lane-ops per second. */
 int orbgpu_measure_popc_peak(int device, double *popc_per_second, double *lop3_per_second);
+/* Issue rate of one instruction kind in lane-operations per second (register-resident loop): mode 0 POPC, 1 LOP3,
+ * 2 VIMNMX3.S16x2, 3 VIMNMX.S16x2, 4 VIADD.16x2, 5 PRMT, 6 IMAD, 7 VIMNMX3 (s32), 8 IADD3. */
+int orbgpu_measure_pipe(int device, int mode, double *ops_per_second);
 
 /* Per-stage device timing (CUDA events on the handle's stream, recorded only while enabled).
  * Stages: 0 pyramid (import + 7 resizes), 1 FAST cells, 2 octree, 3 blur, 4 orientation+descriptor,

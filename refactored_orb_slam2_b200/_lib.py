@@ -65,6 +65,7 @@ SYMBOLS = {
     "orbgpu_top2_merge_device": (_i, [_vp, _i, _i, _vp, _f, _i, _vp, _i, _vp]),
     "orbgpu_hamming_top2_csr": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i]),
     "orbgpu_measure_popc_peak": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "orbgpu_measure_pipe": (_i, [_i, _i, C.POINTER(C.c_double)]),
     "orbgpu_launch_count": (_i64, [_i]),
     "orbgpu_set_profiling": (_i, [_vp, _i]),
     "orbgpu_stage_times": (_i, [_vp, _vp, _i]),

@@ -85,7 +85,7 @@ struct orbgpu_extractor {
   unsigned *dStatus = nullptr;
   int kpCap = 0;
   // stereo results (owned by the LEFT handle)
-  float *dURight = nullptr, *dDepth = nullptr; int *dBestSad = nullptr;
+  float *dURight = nullptr, *dDepth = nullptr; int *dBestSad = nullptr, *dRowStart = nullptr, *dSorted = nullptr;
   cudaEvent_t evDone = nullptr;
   int lastBatch = 0;
   // optional per-stage timing
@@ -455,7 +455,7 @@ void orbgpu_extractor_destroy(orbgpu_extractor *e) {
   DeviceGuard guard(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   void *ptrs[] = {e->dT, e->dTabs, e->dTiles, e->dBlurTiles, e->dRzTiles, e->dInput, e->dPyr, e->dBlur, e->dCand, e->dNodeOf, e->dSel, e->dCandCount,
-                  e->dSelCount, e->dKpCount, e->dKps, e->dDesc, e->dStatus, e->dURight, e->dDepth, e->dBestSad};
+                  e->dSelCount, e->dKpCount, e->dKps, e->dDesc, e->dStatus, e->dURight, e->dDepth, e->dBestSad, e->dRowStart, e->dSorted};
   for (void *q : ptrs) if (q) cudaFree(q);
   if (e->evDone) cudaEventDestroy(e->evDone);
   for (auto &slot : e->evStage) for (auto &p : slot) for (cudaEvent_t ev : p) if (ev) cudaEventDestroy(ev);
@@ -575,8 +575,11 @@ int orbgpu_extract_batch(orbgpu_extractor *e, const uint8_t *images, int count, 
     return ORBGPU_E_CAPACITY;
   }
   DeviceGuard guard(e->device);
-  // tight device copy: rows of `width` bytes
-  if (count == 1 || image_step == (size_t)height * row_step) {
+  // tight device copy: rows of `width` bytes.  Contiguous inputs go as ONE linear copy (2-D copies of odd-width rows
+  // fall off the DMA fast path).
+  if (row_step == (size_t)width && (count == 1 || image_step == (size_t)width * height)) {
+    ORBGPU_CUDA_CHECK(cudaMemcpyAsync(e->dInput, images, (size_t)width * height * count, cudaMemcpyHostToDevice, e->stream));
+  } else if (count == 1 || image_step == (size_t)height * row_step) {
     ORBGPU_CUDA_CHECK(cudaMemcpy2DAsync(e->dInput, width, images, row_step, width, (size_t)height * count,
                                         cudaMemcpyHostToDevice, e->stream));
   } else {
@@ -687,6 +690,9 @@ int orbgpu_stereo_match_device(orbgpu_extractor *L, orbgpu_extractor *R, int fir
     ORBGPU_CUDA_CHECK(cudaMalloc(&L->dURight, n * sizeof(float)));
     ORBGPU_CUDA_CHECK(cudaMalloc(&L->dDepth, n * sizeof(float)));
     ORBGPU_CUDA_CHECK(cudaMalloc(&L->dBestSad, n * sizeof(int)));
+    ORBGPU_CUDA_CHECK(cudaMalloc(&L->dSorted, n * sizeof(int)));
+    ORBGPU_CUDA_CHECK(cudaMalloc(&L->dRowStart, (size_t)L->p.max_batch * (L->p.max_height + 2) * sizeof(int)));
+    ORBGPU_CUDA_CHECK(stereo_configure(L->p.max_height + 1));
   }
   if (R != L) {
     ORBGPU_CUDA_CHECK(cudaEventRecord(R->evDone, R->stream));
@@ -696,7 +702,7 @@ int orbgpu_stereo_match_device(orbgpu_extractor *L, orbgpu_extractor *R, int fir
   A.pyrL = L->dPyr; A.pyrR = R->dPyr; A.kpsL = L->dKps; A.kpsR = R->dKps; A.descL = L->dDesc; A.descR = R->dDesc;
   A.cntL = L->dKpCount; A.cntR = R->dKpCount; A.kpCapL = L->kpCap; A.kpCapR = R->kpCap;
   A.firstL = first_left; A.firstR = first_right; A.pairs = pairs; A.mbf = mbf; A.mb = mb;
-  A.uRight = L->dURight; A.depth = L->dDepth; A.bestSad = L->dBestSad;
+  A.uRight = L->dURight; A.depth = L->dDepth; A.bestSad = L->dBestSad; A.rowStart = L->dRowStart; A.sorted = L->dSorted;
   { StageTimer t(L, 5); ORBGPU_CUDA_CHECK(launch_stereo(L->T, L->dT, A, L->kpCap, L->stream)); }
   if (R != L) {   // the right handle must not overwrite its buffers before the match has read them
     ORBGPU_CUDA_CHECK(cudaEventRecord(L->evDone, L->stream));
@@ -887,6 +893,18 @@ int orbgpu_measure_popc_peak(int device, double *popc_per_second, double *lop3_p
   cudaDeviceProp prop;
   ORBGPU_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
   ORBGPU_CUDA_CHECK(run_popc_microbench(prop.multiProcessorCount, popc_per_second, lop3_per_second));
+  return ORBGPU_OK;
+}
+
+int orbgpu_measure_pipe(int device, int mode, double *ops_per_second) {
+  if (!ops_per_second) { set_error("null output"); return ORBGPU_E_INVALID; }
+  if (orbgpu_device_count() < 1) { set_error("no CUDA device available (this library has no CPU path)"); return ORBGPU_E_CUDA; }
+  DeviceGuard guard(device);
+  int dev = 0;
+  ORBGPU_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  ORBGPU_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  ORBGPU_CUDA_CHECK(run_pipe_probe(prop.multiProcessorCount, mode, ops_per_second));
   return ORBGPU_OK;
 }
 

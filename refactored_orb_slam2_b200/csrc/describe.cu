@@ -6,8 +6,10 @@
 //  * IC_Angle: 31 coalesced row reads of the UNBLURRED level (lane = column u), integer moments
 //    m10 / m01 reduced by shuffles (exact, order-free), then cv::fastAtan2's float polynomial with
 //    round-to-nearest mul/add/div intrinsics (the reference build never fuses into FMAs).
-//  * rBRIEF: lane i builds descriptor byte i from 16 pattern points rotated by (cos, sin) of the
-//    angle.  cosf/sinf replicate glibc's double-precision sincosf algorithm (see sincos_glibc) so
+//  * rBRIEF: the 37 x 37 blurred patch around the keypoint (pattern reach <= 18 px) is first staged in
+//    the warp's shared-memory slot with coalesced 32-bit row loads — the 512 rotated sample positions
+//    are a scatter that would otherwise cost one 32-byte L2 sector per sample; then lane i builds
+//    descriptor byte i from 16 pattern points rotated by (cos, sin) of the angle.  cosf/sinf replicate glibc's double-precision sincosf algorithm (see sincos_glibc) so
 //    that cvRound(x*b + y*a) lands on the same pixel as on the host.
 //  * The keypoint record (cv::KeyPoint layout) and the 32-byte descriptor row go straight to their
 //    final, level-major slot: start = sum of the lower levels' octree counts.
@@ -17,7 +19,6 @@ namespace orbgpu {
 
 namespace {
 
-__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};  // ORBextractor.cc:449-463
 __device__ const signed char d_pattern[1024] = {
 #include "../../include/orb_pattern.inc"
 };
@@ -90,12 +91,16 @@ __device__ __forceinline__ void sincos_glibc(float y, float *sinp, float *cosp) 
 }
 
 constexpr int kWarpsPerCta = 8;
+constexpr int kPatchR = 18;                    // |rotated pattern coordinate| <= round(13 * sqrt 2) = 18 < EDGE_THRESHOLD
+constexpr int kPatchRows = 2 * kPatchR + 1;    // 37
+constexpr int kPatchWords = 11;                // 44 bytes per staged row: up to 3 alignment bytes + 37 + slack
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur,
            const int4 *__restrict__ selAll, const int *__restrict__ selCount, orbgpu_keypoint *__restrict__ kps,
            uint8_t *__restrict__ desc, int *__restrict__ kpCount, unsigned *__restrict__ status) {
   __shared__ signed char sPat[1024];
+  __shared__ __align__(16) unsigned sPatch[kWarpsPerCta][kPatchRows * kPatchWords];
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) sPat[i] = d_pattern[i];
   __syncthreads();
 
@@ -121,19 +126,37 @@ k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, co
   const size_t plane = G.pyrOffset + (size_t)img * G.planeBytes;
   const uint8_t *centre = pyr + plane + (size_t)(s.y + kEdge) * G.pitch + (s.x + kEdge);
 
+  // ---- every global load of this keypoint is issued up front (31 orientation rows + 13 patch words per lane), so a
+  // warp pays one memory latency instead of one per row
+  static constexpr int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};   // ORBextractor.cc:449-463
+  const int u = lane - kHalfPatch;
+  const int au = abs(u);
+  int ring[2 * kHalfPatch + 1];
+#pragma unroll
+  for (int i = 0; i <= 2 * kHalfPatch; i++) {
+    const int v = i - kHalfPatch;
+    ring[i] = (lane < 31 && au <= kUmax[v < 0 ? -v : v]) ? (int)centre[v * G.pitch + u] : 0;
+  }
+  // blurred patch: rows y-18 .. y+18, from the 4-byte aligned column at or before x-18
+  unsigned *patch = sPatch[threadIdx.x >> 5];
+  const int px0 = s.x + kEdge - kPatchR;                       // padded column of the patch's first pixel
+  const int lead = px0 & 3;
+  const uint8_t *src = blur + plane + (size_t)(s.y + kEdge - kPatchR) * G.pitch + (px0 - lead);
+  constexpr int kPatchIters = (kPatchRows * kPatchWords + 31) / 32;
+  unsigned pw[kPatchIters];
+#pragma unroll
+  for (int k = 0; k < kPatchIters; k++) {
+    const int i = lane + 32 * k;
+    const int r = i / kPatchWords, j = i - r * kPatchWords;
+    pw[k] = i < kPatchRows * kPatchWords ? *reinterpret_cast<const unsigned *>(src + (size_t)r * G.pitch + 4 * j) : 0u;
+  }
+
   // ---- IC_Angle
   int m10 = 0, m01 = 0;
-  const int u = lane - kHalfPatch;
-  if (lane < 31) {
-    const int au = abs(u);
-#pragma unroll 1
-    for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
-      if (au <= c_umax[abs(v)]) {
-        const int val = centre[v * G.pitch + u];
-        m10 += u * val;
-        m01 += v * val;
-      }
-    }
+#pragma unroll
+  for (int i = 0; i <= 2 * kHalfPatch; i++) {
+    m10 += u * ring[i];
+    m01 += (i - kHalfPatch) * ring[i];
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -146,7 +169,13 @@ k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, co
   const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
   float a, b;
   sincos_glibc(__fmul_rn(angle, factorPI), &b, &a);   // a = cos, b = sin
-  const uint8_t *bc = blur + plane + (size_t)(s.y + kEdge) * G.pitch + (s.x + kEdge);
+#pragma unroll
+  for (int k = 0; k < kPatchIters; k++) {
+    const int i = lane + 32 * k;
+    if (i < kPatchRows * kPatchWords) patch[i] = pw[k];
+  }
+  __syncwarp();
+  const uint8_t *bc = reinterpret_cast<const uint8_t *>(patch) + kPatchR * (kPatchWords * 4) + lead + kPatchR;
   const signed char *p = sPat + lane * 32;     // 16 pattern points (x, y) per descriptor byte
   unsigned val = 0;
 #pragma unroll
@@ -157,7 +186,7 @@ k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, co
       const float px = (float)p[2 * e], py = (float)p[2 * e + 1];
       const int ry = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
       const int rx = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
-      t[e] = bc[ry * G.pitch + rx];
+      t[e] = bc[ry * (kPatchWords * 4) + rx];
     }
     val |= (unsigned)(t[0] < t[1]) << bit;
   }

@@ -51,12 +51,16 @@ __device__ __forceinline__ unsigned pair_at(unsigned w0, unsigned w1, unsigned w
 }
 
 // Arc margins (packed s16x2) of the two pixels at window bytes C, C+1; rows[r] = window words of image row y-3+r.
+// Differences are kept biased, d' = ring - centre + 256 in [1, 511] per half: both halves stay positive, so the 32
+// subtractions are plain 32-bit multiply-adds (FMA pipe) with no carry between halves, leaving the half-rate ALU
+// pipe to the 160 packed min/max; the bias is removed from the two arc extrema at the end.
 template <int C>
 __device__ __forceinline__ unsigned margin_pair(const unsigned (&w)[7][3]) {
-  const unsigned negc = __vneg2(pair_at<C>(w[3][0], w[3][1], w[3][2]));
+  const unsigned bias = 0x01000100u - pair_at<C>(w[3][0], w[3][1], w[3][2]);   // 256 - centre per half, no borrow
+  const unsigned one = 1u;
   unsigned d[16];
   // ring order of cv::FAST 9/16: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
-#define RING(k, dx, dy) d[k] = __vadd2(pair_at<C + (dx)>(w[3 + (dy)][0], w[3 + (dy)][1], w[3 + (dy)][2]), negc)
+#define RING(k, dx, dy) d[k] = pair_at<C + (dx)>(w[3 + (dy)][0], w[3 + (dy)][1], w[3 + (dy)][2]) * one + bias
   RING(0, 0, 3);   RING(1, 1, 3);   RING(2, 2, 2);    RING(3, 3, 1);
   RING(4, 3, 0);   RING(5, 3, -1);  RING(6, 2, -2);   RING(7, 1, -3);
   RING(8, 0, -3);  RING(9, -1, -3); RING(10, -2, -2); RING(11, -3, -1);
@@ -68,7 +72,7 @@ __device__ __forceinline__ unsigned margin_pair(const unsigned (&w)[7][3]) {
     a3[k] = mn3(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
     b3[k] = mx3(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
   }
-  unsigned bright = 0x80008000u, darkNeg = 0x7fff7fffu;
+  unsigned bright = 0u, darkNeg = 0x7fff7fffu;
 #pragma unroll
   for (int k = 0; k < 16; k += 2) {
     const unsigned a9 = mn3(a3[k], a3[(k + 3) & 15], a3[(k + 6) & 15]);
@@ -78,66 +82,100 @@ __device__ __forceinline__ unsigned margin_pair(const unsigned (&w)[7][3]) {
     const unsigned b9b = mx3(b3[k + 1], b3[(k + 4) & 15], b3[(k + 7) & 15]);
     darkNeg = mn3(darkNeg, b9, b9b);
   }
-  return mx2(bright, __vneg2(darkNeg));
+  // bright margin = bright - 256, dark margin = 256 - darkNeg  (each within [-255, 255])
+  return mx2(__vsub2(bright, 0x01000100u), __vsub2(0x01000100u, darkNeg));
 }
 
-// tiles[t] = (level, cell row i, first cell column j0, cell count)
-__global__ void __launch_bounds__(kThreads)
+// Geometry of one work item = one tile of one image.
+struct TileGeom {
+  int level, img, X0, Y0, TW, TH, gx0, offL, groups, bx, lead;
+};
+__device__ __forceinline__ TileGeom tile_geom(const LevelTable *T, const int4 *tiles, int ntiles, int item) {
+  TileGeom t;
+  const int ti = item % ntiles;
+  t.img = item / ntiles;
+  const int4 tile = tiles[ti];                            // (level, cell row i, first cell column j0, cell count)
+  t.level = tile.x;
+  const LevelGeom &G = T->lv[t.level];
+  // detection rectangle of the tile, level coordinates
+  t.X0 = kEdge + tile.z * G.wCell; t.Y0 = kEdge + tile.y * G.hCell;
+  const int X1 = min(kEdge + (tile.z + tile.w) * G.wCell, G.w - kEdge);
+  const int Y1 = min(t.Y0 + G.hCell, G.h - kEdge);
+  t.TW = X1 - t.X0; t.TH = Y1 - t.Y0;
+  // 4-pixel groups on the padded plane's 4-byte grid
+  t.gx0 = (t.X0 + kEdge) & ~3;                            // padded column of the first group
+  t.offL = (t.X0 + kEdge) - t.gx0;                        // tile x = score column - offL
+  t.groups = (t.offL + t.TW + 3) >> 2;
+  t.bx = (t.gx0 - 4) & ~15;                               // window origin: 16-byte aligned for TMA
+  t.lead = (t.gx0 - 4) - t.bx;                            // 0, 4, 8 or 12
+  return t;
+}
+
+// Persistent CTAs: each walks items blockIdx.x, blockIdx.x + gridDim.x, ... with a two-stage window ring, so the TMA
+// copy of the next tile is in flight while the current one is processed.
+__global__ void __launch_bounds__(kThreads, 4)
 k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict__ T, const int4 *__restrict__ tiles,
-             Cand *__restrict__ cand, int *__restrict__ candCount, unsigned *__restrict__ status, const FastConfig cfg) {
+             int ntiles, int totalItems, Cand *__restrict__ cand, int *__restrict__ candCount,
+             unsigned *__restrict__ status, const FastConfig cfg) {
   extern __shared__ uint8_t smemRaw[];
-  __shared__ __align__(8) unsigned long long sBar;
+  __shared__ __align__(8) unsigned long long sBar[2];
   __shared__ int sCellCnt[kFastCellsPerTile];
   __shared__ int sEmit, sBase, sQueued, sKept, sOut;
 
-  const int4 tile = tiles[blockIdx.x];
-  const int level = tile.x, ci = tile.y, cj0 = tile.z, nc = tile.w;
-  const LevelGeom &G = T->lv[level];
-  const int img = blockIdx.y;
   const int iniTh = T->iniTh, minTh = T->minTh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  // detection rectangle of the tile, level coordinates
-  const int X0 = kEdge + cj0 * G.wCell, Y0 = kEdge + ci * G.hCell;
-  const int X1 = min(kEdge + (cj0 + nc) * G.wCell, G.w - kEdge);
-  const int Y1 = min(Y0 + G.hCell, G.h - kEdge);
-  const int TW = X1 - X0, TH = Y1 - Y0;
-  if (TW <= 0 || TH <= 0) return;
-
   uint8_t *smem = smemRaw + ((128u - (smem_u32(smemRaw) & 127u)) & 127u);   // TMA destination: 128-byte aligned
-  uint8_t *sImg = smem;                                   // fastBoxW x fastBoxH window
-  uint8_t *sScore = smem + cfg.imgBytes;                  // u8 scores, pitch cfg.scorePitch, column 0 = padded column gx0
+  uint8_t *sScore = smem + 2 * cfg.imgBytes;              // u8 scores, pitch cfg.scorePitch, column 0 = padded column gx0
   Cand *sStage = reinterpret_cast<Cand *>(sScore + cfg.scoreBytes);
   unsigned short *sQueue = reinterpret_cast<unsigned short *>(sStage + cfg.stageCap);   // (row << 8 | column) of non-zero scores
-  const int bw = G.fastBoxW, sp = cfg.scorePitch;
-  // 4-pixel groups on the padded plane's 4-byte grid
-  const int gx0 = (X0 + kEdge) & ~3;                      // padded column of the first group
-  const int offL = (X0 + kEdge) - gx0;                    // tile x = score column - offL
-  const int groups = (offL + TW + 3) >> 2;
-  const int bx = (gx0 - 4) & ~15;                         // window origin: 16-byte aligned for TMA
-  const int lead = (gx0 - 4) - bx;                        // 0, 4, 8 or 12
+  const int sp = cfg.scorePitch;
 
   if (tid == 0) {
-    mbar_init(&sBar, 1);
+    mbar_init(&sBar[0], 1);
+    mbar_init(&sBar[1], 1);
     mbar_fence_init();
-    sEmit = 0; sQueued = 0; sKept = 0; sOut = 0;
   }
-  if (tid < kFastCellsPerTile) sCellCnt[tid] = 0;
   __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(&sBar, (unsigned)(G.fastBoxW * G.fastBoxH));
-    tma_load_3d(sImg, &maps.m[level], bx, Y0 - 3 + kEdge, img, &sBar);
+  if (tid == 0 && (int)blockIdx.x < totalItems) {
+    const TileGeom n = tile_geom(T, tiles, ntiles, blockIdx.x);
+    const LevelGeom &Gn = T->lv[n.level];
+    mbar_expect_tx(&sBar[0], (unsigned)(Gn.fastBoxW * Gn.fastBoxH));
+    tma_load_3d(smem, &maps.m[n.level], n.bx, n.Y0 - 3 + kEdge, n.img, &sBar[0]);
   }
-  mbar_wait(&sBar, 0);
 
-  // ---- arc margins: a thread owns score columns 4g .. 4g+3 of row y; corners at minTh are queued
-  const unsigned th2 = (unsigned)minTh * 0x00010001u;
-  for (int y0 = 0; y0 < TH; y0 += kWarps) {
-    const int y = y0 + warp;
-    for (int g0 = 0; g0 < groups; g0 += 32) {
-      const int g = g0 + lane;
+  int iter = 0;
+  for (int item = blockIdx.x; item < totalItems; item += gridDim.x, iter++) {
+    const int stage = iter & 1;
+    const TileGeom tg = tile_geom(T, tiles, ntiles, item);
+    const LevelGeom &G = T->lv[tg.level];
+    const int level = tg.level, img = tg.img, X0 = tg.X0, Y0 = tg.Y0, TW = tg.TW, TH = tg.TH;
+    const int offL = tg.offL, groups = tg.groups, lead = tg.lead;
+    const uint8_t *sImg = smem + stage * cfg.imgBytes;    // fastBoxW x fastBoxH window of this item
+    const int bw = G.fastBoxW;
+    if (tid == 0) {
+      sEmit = 0; sQueued = 0; sKept = 0; sOut = 0;
+      const int next = item + gridDim.x;
+      if (next < totalItems) {                            // the other stage was released by the barrier ending the last item
+        const TileGeom n = tile_geom(T, tiles, ntiles, next);
+        const LevelGeom &Gn = T->lv[n.level];
+        mbar_expect_tx(&sBar[stage ^ 1], (unsigned)(Gn.fastBoxW * Gn.fastBoxH));
+        tma_load_3d(smem + (stage ^ 1) * cfg.imgBytes, &maps.m[n.level], n.bx, n.Y0 - 3 + kEdge, n.img, &sBar[stage ^ 1]);
+      }
+    }
+    if (tid < kFastCellsPerTile) sCellCnt[tid] = 0;
+    __syncthreads();
+    mbar_wait(&sBar[stage], (iter >> 1) & 1);
+
+    // ---- arc margins: work items = (row, 4-pixel group) pairs, dealt round-robin to the CTA's threads so that every
+    // lane is busy whatever the tile shape; corners at minTh are queued
+    const unsigned th2 = (unsigned)minTh * 0x00010001u;
+    const int items = TH * groups;
+    const int stepY = kThreads / groups, stepG = kThreads - stepY * groups;
+    int y = tid / groups, g = tid - y * groups;
+    const unsigned ltMask = (1u << lane) - 1u;
+    for (int i0 = 0; i0 < items; i0 += kThreads) {
       unsigned packed = 0;
-      if (y < TH && g < groups) {
+      if (i0 + tid < items) {
         unsigned w[7][3];
 #pragma unroll
         for (int r = 0; r < 7; r++) {
@@ -154,26 +192,24 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
         if (hi < 4) packed &= 0xffffffffu >> (8 * (4 - hi));
         *reinterpret_cast<unsigned *>(sScore + y * sp + 4 * g) = packed;
       }
-      // queue the non-zero scores: warp-aggregated reservation, (row << 8 | score column) entries
-      const int mine = (packed & 0xffu ? 1 : 0) + (packed & 0xff00u ? 1 : 0) + (packed & 0xff0000u ? 1 : 0) + (packed >> 24 ? 1 : 0);
-      int incl = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      if (total) {
+      // queue the non-zero scores as (row << 8 | score column): one ballot per byte lane, one reservation per warp
+      if (__any_sync(0xffffffffu, packed != 0u)) {
+        const unsigned b0 = __ballot_sync(0xffffffffu, packed & 0xffu), b1 = __ballot_sync(0xffffffffu, packed & 0xff00u);
+        const unsigned b2 = __ballot_sync(0xffffffffu, packed & 0xff0000u), b3 = __ballot_sync(0xffffffffu, packed >> 24);
+        const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2);
         int base = 0;
-        if (lane == 31) base = atomicAdd(&sQueued, total);
-        base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-          if ((packed >> (8 * k)) & 0xffu) sQueue[base++] = (unsigned short)((y << 8) | (4 * g + k));
+        if (lane == 0) base = atomicAdd(&sQueued, n0 + n1 + n2 + __popc(b3));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned short e = (unsigned short)((y << 8) | (4 * g));
+        if (packed & 0xffu) sQueue[base + __popc(b0 & ltMask)] = e;
+        if (packed & 0xff00u) sQueue[base + n0 + __popc(b1 & ltMask)] = e + 1;
+        if (packed & 0xff0000u) sQueue[base + n0 + n1 + __popc(b2 & ltMask)] = e + 2;
+        if (packed >> 24) sQueue[base + n0 + n1 + n2 + __popc(b3 & ltMask)] = e + 3;
       }
+      y += stepY; g += stepG;
+      if (g >= groups) { g -= groups; y++; }
     }
-  }
-  __syncthreads();
+    __syncthreads();
 
   // ---- NMS inside each cell's rectangle over the queue; survivors go to the stage list, cells count survivors at iniTh
   const int iniS = iniTh - minTh;                         // score > iniS  <=>  margin > iniTh
@@ -228,6 +264,8 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
       if (slot < G.candCap) out[slot] = o;
     }
   }
+    __syncthreads();   // stage list, queue, counters and this item's window are free again
+  }
 }
 
 }  // namespace
@@ -250,15 +288,19 @@ FastConfig fast_make_config(const LevelTable &T) {
   c.scoreBytes = (c.scorePitch * hMax + 15) & ~15;
   c.stageCap = (tw / 2 + 1) * (hMax / 2 + 1);      // bound on strict 8-neighbour maxima in a tile
   c.queueCap = c.scorePitch * hMax;
-  c.smemBytes = 128 + c.imgBytes + c.scoreBytes + c.stageCap * (int)sizeof(Cand) + c.queueCap * 2;
+  c.smemBytes = 128 + 2 * c.imgBytes + c.scoreBytes + c.stageCap * (int)sizeof(Cand) + c.queueCap * 2;
   c.maxIters = ((hMax + kWarps - 1) / kWarps) * (((tw + 6 + 3) / 4 + 31) / 32);
   return c;
 }
 
 cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &maps, const int4 *tiles, int ntiles,
                         const FastConfig &c, int batch, cudaStream_t s) {
-  dim3 grid(ntiles, batch);
-  k_fast_cells<<<grid, kThreads, c.smemBytes, s>>>(maps, B.dT, tiles, B.cand, B.candCount, B.status, c);
+  const int total = ntiles * batch;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = total < 4 * sms ? total : 4 * sms;
+  k_fast_cells<<<grid, kThreads, c.smemBytes, s>>>(maps, B.dT, tiles, ntiles, total, B.cand, B.candCount, B.status, c);
   count_launch();
   return cudaGetLastError();
 }

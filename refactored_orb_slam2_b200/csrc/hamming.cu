@@ -220,18 +220,27 @@ __global__ void k_pair_distance(const uint8_t *__restrict__ a, const uint8_t *__
 }
 
 // Register-resident issue-rate probes: 8 independent dependency chains per thread.
+// modes: 0 POPC, 1 LOP3, 2 VIMNMX3.S16x2, 3 VIMNMX.S16x2, 4 VIADD.16x2, 5 PRMT, 6 IMAD, 7 VIMNMX3 (s32), 8 IADD3
 template <int MODE>
 __global__ void __launch_bounds__(256) k_pipe_probe(unsigned *out, int iters, unsigned seed) {
   unsigned v[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) v[j] = seed * (threadIdx.x + 1) + j * 0x9e3779b9u;
+  const unsigned a = seed ^ 0x5bd1e995u, b = seed * 3u + 1u;
   for (int i = 0; i < iters; i++) {
 #pragma unroll
     for (int u = 0; u < 4; u++) {
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         if (MODE == 0) asm volatile("popc.b32 %0, %0;" : "+r"(v[j]));
-        else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(seed), "r"(i));
+        else if (MODE == 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[j]) : "r"(a), "r"(b));
+        else if (MODE == 2) v[j] = (u & 1) ? __vimin3_s16x2(v[j], v[(j + 1) & 7], v[(j + 2) & 7]) : __vimax3_s16x2(v[j], v[(j + 3) & 7], v[(j + 5) & 7]);
+        else if (MODE == 3) v[j] = (u & 1) ? __vmins2(v[j], v[(j + 1) & 7]) : __vmaxs2(v[j], v[(j + 3) & 7]);
+        else if (MODE == 4) asm volatile("add.s16x2 %0, %0, %1;" : "+r"(v[j]) : "r"(a));
+        else if (MODE == 5) asm volatile("prmt.b32 %0, %0, %1, 0x4140;" : "+r"(v[j]) : "r"(a));
+        else if (MODE == 6) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v[j]) : "r"(a), "r"(b));
+        else if (MODE == 7) v[j] = (u & 1) ? (unsigned)__vimin3_s32((int)v[j], (int)v[(j + 1) & 7], (int)v[(j + 2) & 7]) : (unsigned)__vimax3_s32((int)v[j], (int)v[(j + 3) & 7], (int)v[(j + 5) & 7]);
+        else asm volatile("{.reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2;}" : "+r"(v[j]) : "r"(a), "r"(b));
       }
     }
   }
@@ -306,7 +315,11 @@ cudaError_t launch_pair_distance(const uint8_t *a, const uint8_t *b, int n, int 
   return cudaGetLastError();
 }
 
-cudaError_t run_popc_microbench(int smCount, double *popcPerSec, double *lop3PerSec) {
+template <int MODE>
+static void launch_probe(int blocks, unsigned *out, int iters, unsigned seed) { k_pipe_probe<MODE><<<blocks, 256>>>(out, iters, seed); }
+
+// Lane-operations per second of one instruction kind (see k_pipe_probe for the mode numbers).
+cudaError_t run_pipe_probe(int smCount, int mode, double *opsPerSec) {
   unsigned *out = nullptr;
   cudaError_t e = cudaMalloc(&out, 4);
   if (e != cudaSuccess) return e;
@@ -314,30 +327,39 @@ cudaError_t run_popc_microbench(int smCount, double *popcPerSec, double *lop3Per
   cudaEventCreate(&a);
   cudaEventCreate(&b);
   const int iters = 4096, blocks = smCount * 8;
-  double res[2] = {0, 0};
-  for (int mode = 0; mode < 2; mode++) {
-    float best = 1e30f;
-    for (int rep = 0; rep < 4; rep++) {
-      cudaEventRecord(a);
-      if (mode == 0) k_pipe_probe<0><<<blocks, 256>>>(out, iters, 12345u + rep);
-      else k_pipe_probe<1><<<blocks, 256>>>(out, iters, 12345u + rep);
-      cudaEventRecord(b);
-      e = cudaEventSynchronize(b);
-      if (e != cudaSuccess) break;
-      float ms = 0;
-      cudaEventElapsedTime(&ms, a, b);
-      if (rep > 0 && ms < best) best = ms;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(a);
+    switch (mode) {
+      case 0: launch_probe<0>(blocks, out, iters, 12345u + rep); break;
+      case 1: launch_probe<1>(blocks, out, iters, 12345u + rep); break;
+      case 2: launch_probe<2>(blocks, out, iters, 12345u + rep); break;
+      case 3: launch_probe<3>(blocks, out, iters, 12345u + rep); break;
+      case 4: launch_probe<4>(blocks, out, iters, 12345u + rep); break;
+      case 5: launch_probe<5>(blocks, out, iters, 12345u + rep); break;
+      case 6: launch_probe<6>(blocks, out, iters, 12345u + rep); break;
+      case 7: launch_probe<7>(blocks, out, iters, 12345u + rep); break;
+      default: launch_probe<8>(blocks, out, iters, 12345u + rep); break;
     }
+    cudaEventRecord(b);
+    e = cudaEventSynchronize(b);
     if (e != cudaSuccess) break;
-    res[mode] = (double)blocks * 256.0 * iters * 32.0 / (best * 1e-3);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0 && ms < best) best = ms;
   }
   cudaEventDestroy(a);
   cudaEventDestroy(b);
   cudaFree(out);
   if (e != cudaSuccess) return e;
-  *popcPerSec = res[0];
-  *lop3PerSec = res[1];
+  *opsPerSec = (double)blocks * 256.0 * iters * 32.0 / (best * 1e-3);
   return cudaGetLastError();
+}
+
+cudaError_t run_popc_microbench(int smCount, double *popcPerSec, double *lop3PerSec) {
+  cudaError_t e = run_pipe_probe(smCount, 0, popcPerSec);
+  if (e != cudaSuccess) return e;
+  return run_pipe_probe(smCount, 1, lop3PerSec);
 }
 
 }  // namespace orbgpu

@@ -141,7 +141,10 @@ struct StereoArgs {
   float mbf, mb;
   float *uRight, *depth;    // [pairs][kpCapL] (indexed from 0, i.e. relative to firstL)
   int *bestSad;             // [pairs][kpCapL]
+  int *rowStart;            // [pairs][rows + 1]: right keypoints bucketed by image row
+  int *sorted;              // [pairs][kpCapR]
 };
+cudaError_t stereo_configure(int rows);
 cudaError_t launch_stereo(const LevelTable &T, const LevelTable *dT, const StereoArgs &A, int maxKp, cudaStream_t s);
 
 struct Top2Rec { int d1, d2; long long idx; };   // 16 bytes, the shard exchange unit
@@ -156,5 +159,6 @@ cudaError_t launch_hamming_csr(const uint8_t *q, int nq, const uint8_t *train, c
                                const int *cand, int *idx1, int *d1, int *d2, cudaStream_t s);
 cudaError_t launch_pair_distance(const uint8_t *a, const uint8_t *b, int n, int *dist, cudaStream_t s);
 cudaError_t run_popc_microbench(int smCount, double *popcPerSec, double *lop3PerSec);
+cudaError_t run_pipe_probe(int smCount, int mode, double *opsPerSec);
 
 }  // namespace orbgpu

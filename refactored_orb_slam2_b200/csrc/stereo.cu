@@ -1,11 +1,13 @@
 // Frame::ComputeStereoMatches (Frame.cc:477-646) on the device-resident outputs of two extract calls.
 //
+// k_stereo_rows — one CTA per pair: counting sort of the right keypoints by image row (int)yR
+//     (histogram, scan, scatter), the device form of the reference's vRowIndices table.
 // k_stereo_match — one warp per LEFT keypoint:
-//   * candidate scan.  The reference buckets right keypoints by image row (vRowIndices) and scans
-//     the bucket of row (size_t)vL in ascending iR; bucket membership is
-//     floor(yR - r) <= row <= ceil(yR + r), r = 2*scale[octR] (Frame.cc:493-502).  Lanes stride over
-//     all right keypoints applying that predicate plus the octave and u-range gates
-//     (Frame.cc:540-545); each lane keeps its first minimum, a shuffle reduction on
+//   * candidate scan.  The reference scans the bucket of row (size_t)vL in ascending iR; a right
+//     keypoint belongs to that bucket iff floor(yR - r) <= row <= ceil(yR + r), r = 2*scale[octR]
+//     (Frame.cc:493-502).  Lanes stride over the sorted right keypoints whose own row lies within
+//     +-(ceil(2*scale_max) + 2) of the left row (a superset), apply that exact predicate plus the
+//     octave and u-range gates (Frame.cc:540-545) and keep their minimum; a shuffle reduction on
 //     (distance, iR) lexicographic order reproduces the sequential strict-'<' scan.
 //   * 11 x 11 SAD at 11 offsets on the keypoint's pyramid level (Frame.cc:557-600): patches are
 //     centre-subtracted integers, the L1 norm is exact in int; lanes split the 121 pixels.
@@ -14,6 +16,8 @@
 // k_stereo_filter — one CTA per pair: median of the matched SADs by a two-level (high byte, low
 //     byte) histogram select — the same value as sort()[size/2].first — then every match with
 //     SAD >= 1.5f*1.4f*median is withdrawn (Frame.cc:634-645).
+#include <cmath>
+
 #include "internal.cuh"
 
 namespace orbgpu {
@@ -29,19 +33,60 @@ __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const 
 
 constexpr int kWarps = 8;
 
+// rowStart[pair][rows + 1], sorted[pair][kpCapR]: right keypoint indices grouped by (int)y
+__global__ void __launch_bounds__(256)
+k_stereo_rows(StereoArgs A, int rows) {
+  extern __shared__ int sHist[];                 // rows + 1 counters, then a running cursor per row
+  __shared__ int sWarpSum[8];
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int imgR = A.firstR + pair;
+  const int nR = A.cntR[imgR];
+  const orbgpu_keypoint *kR = A.kpsR + (size_t)imgR * A.kpCapR;
+  int *rowStart = A.rowStart + (size_t)pair * (rows + 1);
+  int *sorted = A.sorted + (size_t)pair * A.kpCapR;
+  for (int i = tid; i <= rows; i += 256) sHist[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < nR; i += 256) atomicAdd(&sHist[min(max((int)kR[i].y, 0), rows - 1)], 1);
+  __syncthreads();
+  // exclusive scan of rows + 1 counters: contiguous chunk per thread, warp scan, scan of warp totals
+  const int per = (rows + 1 + 255) / 256;
+  const int lo = min(tid * per, rows + 1), hi = min(lo + per, rows + 1);
+  int sum = 0;
+  for (int i = lo; i < hi; i++) sum += sHist[i];
+  int inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) sWarpSum[warp] = inc;
+  __syncthreads();
+  int warpBase = 0;
+  for (int w = 0; w < warp; w++) warpBase += sWarpSum[w];
+  int run = warpBase + inc - sum;
+  for (int i = lo; i < hi; i++) { const int v = sHist[i]; sHist[i] = run; rowStart[i] = run; run += v; }
+  __syncthreads();
+  for (int i = tid; i < nR; i += 256) {
+    const int r = min(max((int)kR[i].y, 0), rows - 1);
+    sorted[atomicAdd(&sHist[r], 1)] = i;
+  }
+}
+
 __global__ void __launch_bounds__(kWarps * 32)
-k_stereo_match(const LevelTable *__restrict__ T, StereoArgs A) {
+k_stereo_match(const LevelTable *__restrict__ T, StereoArgs A, int rows, int rowReach) {
   const int pair = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int iL = blockIdx.x * kWarps + (threadIdx.x >> 5);
   const int imgL = A.firstL + pair, imgR = A.firstR + pair;
-  const int nL = A.cntL[imgL], nR = A.cntR[imgR];
+  const int nL = A.cntL[imgL];
   if (iL >= nL) return;
   const size_t outIdx = (size_t)pair * A.kpCapL + iL;
   const orbgpu_keypoint *kL = A.kpsL + (size_t)imgL * A.kpCapL;
   const orbgpu_keypoint *kR = A.kpsR + (size_t)imgR * A.kpCapR;
   const uint4 *dL = reinterpret_cast<const uint4 *>(A.descL + ((size_t)imgL * A.kpCapL + iL) * 32);
   const uint4 *dR = reinterpret_cast<const uint4 *>(A.descR + (size_t)imgR * A.kpCapR * 32);
+  const int *rowStart = A.rowStart + (size_t)pair * (rows + 1);
+  const int *sorted = A.sorted + (size_t)pair * A.kpCapR;
 
   float uRight = -1.0f, depth = -1.0f;
   int sadOut = -1;
@@ -56,7 +101,9 @@ k_stereo_match(const LevelTable *__restrict__ T, StereoArgs A) {
   int bestDist = kThHigh, bestR = 0x7fffffff;
   if (!(maxU < 0)) {
     const uint4 a0 = dL[0], a1 = dL[1];
-    for (int iR = lane; iR < nR; iR += 32) {
+    const int cLo = rowStart[min(max(rowL - rowReach, 0), rows)], cHi = rowStart[min(max(rowL + rowReach + 1, 0), rows)];
+    for (int c = cLo + lane; c < cHi; c += 32) {
+      const int iR = sorted[c];
       const orbgpu_keypoint kr = kR[iR];
       const float r = __fmul_rn(2.0f, T->lv[kr.octave].scale);
       const int maxr = (int)ceilf(__fadd_rn(kr.y, r)), minr = (int)floorf(__fsub_rn(kr.y, r));
@@ -64,7 +111,7 @@ k_stereo_match(const LevelTable *__restrict__ T, StereoArgs A) {
       if (kr.octave < levelL - 1 || kr.octave > levelL + 1) continue;
       if (!(kr.x >= minU && kr.x <= maxU)) continue;
       const int d = hamming256(a0, a1, dR[2 * iR], dR[2 * iR + 1]);
-      if (d < bestDist) { bestDist = d; bestR = iR; }
+      if (d < bestDist || (d == bestDist && iR < bestR)) { bestDist = d; bestR = iR; }
     }
   }
 #pragma unroll
@@ -192,11 +239,22 @@ k_stereo_filter(StereoArgs A) {
 
 }  // namespace
 
+cudaError_t stereo_configure(int rows) {
+  return cudaFuncSetAttribute(k_stereo_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (rows + 1) * (int)sizeof(int));
+}
+
 cudaError_t launch_stereo(const LevelTable &T, const LevelTable *dT, const StereoArgs &A, int maxKp, cudaStream_t s) {
-  dim3 grid((maxKp + kWarps - 1) / kWarps, A.pairs);
-  k_stereo_match<<<grid, kWarps * 32, 0, s>>>(dT, A);
+  const int rows = T.lv[0].h;
+  // a right keypoint at row yR reaches rows floor(yR - r) .. ceil(yR + r), r <= 2 * scale of the top level
+  const int rowReach = (int)std::ceil(2.0f * T.lv[T.nlevels - 1].scale) + 2;
+  k_stereo_rows<<<A.pairs, 256, (rows + 1) * sizeof(int), s>>>(A, rows);
   count_launch();
   cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  dim3 grid((maxKp + kWarps - 1) / kWarps, A.pairs);
+  k_stereo_match<<<grid, kWarps * 32, 0, s>>>(dT, A, rows, rowReach);
+  count_launch();
+  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   k_stereo_filter<<<A.pairs, 256, 0, s>>>(A);
   count_launch();

@@ -42,7 +42,7 @@ __device__ __forceinline__ unsigned pair_at(unsigned w0, unsigned w1, unsigned w
 // tiles[t] = (level, tile x, tile y, 0)
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_blur(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict__ T, const int4 *__restrict__ tiles, int ntiles,
-       uint8_t *__restrict__ blur) {
+       uint8_t *__restrict__ blur, int imgBase) {
   extern __shared__ uint8_t smemRaw[];
   __shared__ __align__(8) unsigned long long sBar[kWarpsPerCta];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -50,7 +50,7 @@ k_blur(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict__ T, c
   if (t >= ntiles) return;
   const int4 tile = tiles[t];
   const LevelGeom &G = T->lv[tile.x];
-  const int img = blockIdx.y;
+  const int img = imgBase + blockIdx.y;
   const int x0 = 4 + kTW * tile.y;                  // padded coordinates of the tile's first output column / row
   const int y0 = kEdge + kTH * tile.z;
   uint8_t *slot = smemRaw + ((128u - (smem_u32(smemRaw) & 127u)) & 127u) + warp * kSlotBytes;
@@ -132,9 +132,9 @@ void blur_make_tiles(const LevelTable &T, std::vector<int4> &tiles) {
 }
 
 cudaError_t launch_blur(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &maps, const int4 *tiles, int ntiles,
-                        int batch, cudaStream_t s) {
+                        int imgBase, int batch, cudaStream_t s) {
   dim3 grid((ntiles + kWarpsPerCta - 1) / kWarpsPerCta, batch);
-  k_blur<<<grid, kWarpsPerCta * 32, blur_smem_bytes(), s>>>(maps, B.dT, tiles, ntiles, B.blur);
+  k_blur<<<grid, kWarpsPerCta * 32, blur_smem_bytes(), s>>>(maps, B.dT, tiles, ntiles, B.blur, imgBase);
   count_launch();
   return cudaGetLastError();
 }

@@ -88,6 +88,10 @@ struct orbgpu_extractor {
   float *dURight = nullptr, *dDepth = nullptr; int *dBestSad = nullptr, *dRowStart = nullptr, *dSorted = nullptr;
   cudaEvent_t evDone = nullptr;
   int lastBatch = 0;
+  // host-buffer pipeline: copy streams + per-chunk events
+  static constexpr int kMaxChunks = 4;
+  cudaStream_t copyIn = nullptr, copyOut = nullptr;
+  cudaEvent_t evChunkIn[kMaxChunks] = {}, evChunkDone[kMaxChunks] = {};
   // optional per-stage timing
   static constexpr int kProfRing = 32;   // batches remembered between two orbgpu_stage_times calls
   bool profiling = false;
@@ -306,34 +310,45 @@ struct StageTimer {
   ~StageTimer() { if (e->profiling) cudaEventRecord(e->evStage[e->profSlot][stage][1], e->stream); }
 };
 
-// The whole ORBextractor::operator() for `batch` device-resident images, asynchronous on e->stream.
-int run_extract(orbgpu_extractor *e, const uint8_t *dImages, int batch, int w, int h, size_t rowStep, size_t imgStep) {
-  int rc = configure(e, w, h);
-  if (rc) return rc;
+// The whole ORBextractor::operator() for images [imgBase, imgBase + batch) of a device-resident batch whose image 0
+// starts at dImages; asynchronous on e->stream.
+int run_extract_range(orbgpu_extractor *e, const uint8_t *dImages, int imgBase, int batch, size_t rowStep, size_t imgStep) {
   const ExtractBuffers B = e->buffers();
   cudaStream_t s = e->stream;
-  ORBGPU_CUDA_CHECK(cudaMemsetAsync(e->dCandCount, 0, sizeof(int) * kMaxLevels * batch, s));
-  ORBGPU_CUDA_CHECK(cudaMemsetAsync(e->dSelCount, 0, sizeof(int) * kMaxLevels * batch, s));
-  ORBGPU_CUDA_CHECK(cudaMemsetAsync(e->dStatus, 0, sizeof(unsigned), s));
+  ORBGPU_CUDA_CHECK(cudaMemsetAsync(e->dCandCount + (size_t)imgBase * kMaxLevels, 0, sizeof(int) * kMaxLevels * batch, s));
+  ORBGPU_CUDA_CHECK(cudaMemsetAsync(e->dSelCount + (size_t)imgBase * kMaxLevels, 0, sizeof(int) * kMaxLevels * batch, s));
+  {
+    StageTimer t(e, 0);
+    ORBGPU_CUDA_CHECK(launch_import_level0(e->T, B, dImages, rowStep, imgStep, imgBase, batch, s));
+    for (int l = 1; l < e->T.nlevels; l++) {
+      if (e->T.lv[l].rzBoxW)
+        ORBGPU_CUDA_CHECK(launch_resize_tiles(e->T, B, e->rzMaps, e->dRzTiles + e->rzTileOff[l], e->rzTileCnt[l], e->rzSlotBytes, imgBase, batch, s));
+      else
+        ORBGPU_CUDA_CHECK(launch_resize_level(e->T, B, l, imgBase, batch, s));
+    }
+    ORBGPU_CUDA_CHECK(launch_fill_borders(e->T, B, 1, imgBase, batch, s));
+  }
+  { StageTimer t(e, 1); ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->fastMaps, e->dTiles, e->ntiles, e->fastCfg, imgBase, batch, s)); }
+  { StageTimer t(e, 2); ORBGPU_CUDA_CHECK(launch_octree(e->T, B, imgBase, batch, e->octSmem, s)); }
+  { StageTimer t(e, 3); ORBGPU_CUDA_CHECK(launch_blur(e->T, B, e->blurMaps, e->dBlurTiles, e->nBlurTiles, imgBase, batch, s)); }
+  { StageTimer t(e, 4); ORBGPU_CUDA_CHECK(launch_describe(e->T, B, imgBase, batch, s)); }
+  return ORBGPU_OK;
+}
+
+void begin_batch(orbgpu_extractor *e) {
   if (e->profiling) {
     e->profSlot = (int)(e->profCount++ % orbgpu_extractor::kProfRing);
     for (bool &r : e->stageRan[e->profSlot]) r = false;
   }
-  {
-    StageTimer t(e, 0);
-    ORBGPU_CUDA_CHECK(launch_import_level0(e->T, B, dImages, rowStep, imgStep, batch, s));
-    for (int l = 1; l < e->T.nlevels; l++) {
-      if (e->T.lv[l].rzBoxW)
-        ORBGPU_CUDA_CHECK(launch_resize_tiles(e->T, B, e->rzMaps, e->dRzTiles + e->rzTileOff[l], e->rzTileCnt[l], e->rzSlotBytes, batch, s));
-      else
-        ORBGPU_CUDA_CHECK(launch_resize_level(e->T, B, l, batch, s));
-    }
-    ORBGPU_CUDA_CHECK(launch_fill_borders(e->T, B, 1, batch, s));
-  }
-  { StageTimer t(e, 1); ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->fastMaps, e->dTiles, e->ntiles, e->fastCfg, batch, s)); }
-  { StageTimer t(e, 2); ORBGPU_CUDA_CHECK(launch_octree(e->T, B, batch, e->octSmem, s)); }
-  { StageTimer t(e, 3); ORBGPU_CUDA_CHECK(launch_blur(e->T, B, e->blurMaps, e->dBlurTiles, e->nBlurTiles, batch, s)); }
-  { StageTimer t(e, 4); ORBGPU_CUDA_CHECK(launch_describe(e->T, B, batch, s)); }
+}
+
+int run_extract(orbgpu_extractor *e, const uint8_t *dImages, int batch, int w, int h, size_t rowStep, size_t imgStep) {
+  int rc = configure(e, w, h);
+  if (rc) return rc;
+  begin_batch(e);
+  ORBGPU_CUDA_CHECK(cudaMemsetAsync(e->dStatus, 0, sizeof(unsigned), e->stream));
+  rc = run_extract_range(e, dImages, 0, batch, rowStep, imgStep);
+  if (rc) return rc;
   e->lastBatch = batch;
   return ORBGPU_OK;
 }
@@ -458,6 +473,10 @@ void orbgpu_extractor_destroy(orbgpu_extractor *e) {
                   e->dSelCount, e->dKpCount, e->dKps, e->dDesc, e->dStatus, e->dURight, e->dDepth, e->dBestSad, e->dRowStart, e->dSorted};
   for (void *q : ptrs) if (q) cudaFree(q);
   if (e->evDone) cudaEventDestroy(e->evDone);
+  for (cudaEvent_t ev : e->evChunkIn) if (ev) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : e->evChunkDone) if (ev) cudaEventDestroy(ev);
+  if (e->copyIn) cudaStreamDestroy(e->copyIn);
+  if (e->copyOut) cudaStreamDestroy(e->copyOut);
   for (auto &slot : e->evStage) for (auto &p : slot) for (cudaEvent_t ev : p) if (ev) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -565,6 +584,8 @@ int orbgpu_download_results(orbgpu_extractor *e, orbgpu_keypoint *keypoints, uin
   return ORBGPU_OK;
 }
 
+// Host-buffer form.  Large batches are cut into chunks that flow through three streams — H2D copy, the kernel
+// sequence, D2H copy — so that the PCIe transfers of chunks k+1 / k-1 overlap the kernels of chunk k.
 int orbgpu_extract_batch(orbgpu_extractor *e, const uint8_t *images, int count, int width, int height, size_t row_step,
                          size_t image_step, orbgpu_keypoint *keypoints, uint8_t *descriptors, int capacity, int32_t *counts) {
   if (!e || !images || !counts) { set_error("null argument"); return ORBGPU_E_INVALID; }
@@ -574,22 +595,66 @@ int orbgpu_extract_batch(orbgpu_extractor *e, const uint8_t *images, int count, 
     set_error("image %dx%d exceeds the handle's max %dx%d", width, height, e->p.max_width, e->p.max_height);
     return ORBGPU_E_CAPACITY;
   }
+  if (capacity < 1 || ((keypoints == nullptr) != (descriptors == nullptr))) { set_error("bad output buffers"); return ORBGPU_E_INVALID; }
   DeviceGuard guard(e->device);
-  // tight device copy: rows of `width` bytes.  Contiguous inputs go as ONE linear copy (2-D copies of odd-width rows
-  // fall off the DMA fast path).
-  if (row_step == (size_t)width && (count == 1 || image_step == (size_t)width * height)) {
-    ORBGPU_CUDA_CHECK(cudaMemcpyAsync(e->dInput, images, (size_t)width * height * count, cudaMemcpyHostToDevice, e->stream));
-  } else if (count == 1 || image_step == (size_t)height * row_step) {
-    ORBGPU_CUDA_CHECK(cudaMemcpy2DAsync(e->dInput, width, images, row_step, width, (size_t)height * count,
-                                        cudaMemcpyHostToDevice, e->stream));
-  } else {
-    for (int i = 0; i < count; i++)
-      ORBGPU_CUDA_CHECK(cudaMemcpy2DAsync(e->dInput + (size_t)i * width * height, width, images + (size_t)i * image_step,
-                                          row_step, width, height, cudaMemcpyHostToDevice, e->stream));
-  }
-  int rc = run_extract(e, e->dInput, count, width, height, width, (size_t)width * height);
+  int rc = configure(e, width, height);
   if (rc) return rc;
-  return orbgpu_download_results(e, keypoints, descriptors, capacity, counts);
+  if (!e->copyIn) {
+    ORBGPU_CUDA_CHECK(cudaStreamCreateWithFlags(&e->copyIn, cudaStreamNonBlocking));
+    ORBGPU_CUDA_CHECK(cudaStreamCreateWithFlags(&e->copyOut, cudaStreamNonBlocking));
+    for (auto &ev : e->evChunkIn) ORBGPU_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto &ev : e->evChunkDone) ORBGPU_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  const size_t imgBytes = (size_t)width * height;
+  const int chunks = count >= 64 ? orbgpu_extractor::kMaxChunks : count >= 16 ? 2 : 1;
+  const int per = (count + chunks - 1) / chunks;
+  const int cols = std::min(capacity, e->kpCap);
+  begin_batch(e);
+  ORBGPU_CUDA_CHECK(cudaMemsetAsync(e->dStatus, 0, sizeof(unsigned), e->stream));
+  // the copy streams must not run ahead of work already queued on the handle's stream (a previous batch still reading dInput)
+  ORBGPU_CUDA_CHECK(cudaEventRecord(e->evDone, e->stream));
+  ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(e->copyIn, e->evDone, 0));
+  for (int c = 0; c < chunks; c++) {
+    const int first = c * per, n = std::min(per, count - first);
+    if (n <= 0) break;
+    // ---- H2D: tight device copy, rows of `width` bytes.  Contiguous inputs go as ONE linear copy (2-D copies of
+    // odd-width rows fall off the DMA fast path).
+    uint8_t *dst = e->dInput + (size_t)first * imgBytes;
+    const uint8_t *src = images + (size_t)first * image_step;
+    if (row_step == (size_t)width && (n == 1 || image_step == imgBytes)) {
+      ORBGPU_CUDA_CHECK(cudaMemcpyAsync(dst, src, imgBytes * n, cudaMemcpyHostToDevice, e->copyIn));
+    } else if (n == 1 || image_step == (size_t)height * row_step) {
+      ORBGPU_CUDA_CHECK(cudaMemcpy2DAsync(dst, width, src, row_step, width, (size_t)height * n, cudaMemcpyHostToDevice, e->copyIn));
+    } else {
+      for (int i = 0; i < n; i++)
+        ORBGPU_CUDA_CHECK(cudaMemcpy2DAsync(dst + (size_t)i * imgBytes, width, src + (size_t)i * image_step, row_step, width, height,
+                                            cudaMemcpyHostToDevice, e->copyIn));
+    }
+    ORBGPU_CUDA_CHECK(cudaEventRecord(e->evChunkIn[c], e->copyIn));
+    // ---- kernels
+    ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->evChunkIn[c], 0));
+    rc = run_extract_range(e, e->dInput, first, n, width, imgBytes);
+    if (rc) return rc;
+    ORBGPU_CUDA_CHECK(cudaEventRecord(e->evChunkDone[c], e->stream));
+    // ---- D2H: whole rows of the chunk (counts are only known on the device; unused rows are unspecified)
+    ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(e->copyOut, e->evChunkDone[c], 0));
+    ORBGPU_CUDA_CHECK(cudaMemcpyAsync(counts + first, e->dKpCount + first, sizeof(int) * n, cudaMemcpyDeviceToHost, e->copyOut));
+    if (keypoints) {
+      ORBGPU_CUDA_CHECK(cudaMemcpy2DAsync(keypoints + (size_t)first * capacity, (size_t)capacity * sizeof(orbgpu_keypoint),
+                                          e->dKps + (size_t)first * e->kpCap, (size_t)e->kpCap * sizeof(orbgpu_keypoint),
+                                          (size_t)cols * sizeof(orbgpu_keypoint), n, cudaMemcpyDeviceToHost, e->copyOut));
+      ORBGPU_CUDA_CHECK(cudaMemcpy2DAsync(descriptors + (size_t)first * capacity * 32, (size_t)capacity * 32,
+                                          e->dDesc + (size_t)first * e->kpCap * 32, (size_t)e->kpCap * 32, (size_t)cols * 32, n,
+                                          cudaMemcpyDeviceToHost, e->copyOut));
+    }
+  }
+  e->lastBatch = count;
+  ORBGPU_CUDA_CHECK(cudaStreamSynchronize(e->copyOut));
+  rc = check_status(e);
+  if (rc) return rc;
+  for (int i = 0; i < count; i++)
+    if (counts[i] > capacity) { set_error("capacity %d < %d keypoints", capacity, counts[i]); return ORBGPU_E_CAPACITY; }
+  return ORBGPU_OK;
 }
 
 int orbgpu_extract(orbgpu_extractor *e, const uint8_t *image, int width, int height, size_t step, orbgpu_keypoint *keypoints,

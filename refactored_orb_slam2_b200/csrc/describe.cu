@@ -93,38 +93,40 @@ __device__ __forceinline__ void sincos_glibc(float y, float *sinp, float *cosp) 
 constexpr int kWarpsPerCta = 8;
 constexpr int kPatchR = 18;                    // |rotated pattern coordinate| <= round(13 * sqrt 2) = 18 < EDGE_THRESHOLD
 constexpr int kPatchRows = 2 * kPatchR + 1;    // 37
-constexpr int kPatchWords = 11;                // 44 bytes per staged row: up to 3 alignment bytes + 37 + slack
+constexpr int kPatchWords = 10;                // 40 bytes per staged row: up to 3 alignment bytes + 37
+constexpr int kPatchIters = (kPatchRows + 2) / 3;   // three rows of 10 words per warp-wide load
 
+// blockIdx.x = chunk of 8 output slots (level-major keypoint index), blockIdx.y = image
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur,
            const int4 *__restrict__ selAll, const int *__restrict__ selCount, orbgpu_keypoint *__restrict__ kps,
-           uint8_t *__restrict__ desc, int *__restrict__ kpCount, unsigned *__restrict__ status) {
-  __shared__ signed char sPat[1024];
+           uint8_t *__restrict__ desc, int *__restrict__ kpCount, unsigned *__restrict__ status, int imgBase) {
+  __shared__ float2 sPat[512];
   __shared__ __align__(16) unsigned sPatch[kWarpsPerCta][kPatchRows * kPatchWords];
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) sPat[i] = d_pattern[i];
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) sPat[i] = make_float2((float)d_pattern[2 * i], (float)d_pattern[2 * i + 1]);
   __syncthreads();
 
-  const int level = blockIdx.y, img = blockIdx.z;
-  const LevelGeom &G = T->lv[level];
+  const int img = imgBase + blockIdx.y;
   const int lane = threadIdx.x & 31;
-  const int k = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const int slot = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);      // output row of this warp's keypoint
   const int *cnt = selCount + img * kMaxLevels;
-  int start = 0, total = 0;
+  int level = 0, start = 0, total = 0;
   for (int l = 0; l < T->nlevels; l++) {
     const int c = cnt[l];
-    if (l < level) start += c;
+    if (slot >= total + c) { level = l + 1; start = total + c; }
     total += c;
   }
   const int kpCap = T->kpCap;
-  if (level == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     kpCount[img] = min(total, kpCap);
     if (total > kpCap) atomicOr(status, kStatusKpOverflow);
   }
-  if (k >= cnt[level] || start + k >= kpCap) return;
+  if (slot >= total || slot >= kpCap) return;
+  const LevelGeom &G = T->lv[level];
+  const int pitch = G.pitch;
 
-  const int4 s = selAll[G.selOffset + (size_t)img * G.selCap + k];   // x_level, y_level, response
+  const int4 s = selAll[G.selOffset + (size_t)img * G.selCap + (slot - start)];   // x_level, y_level, response
   const size_t plane = G.pyrOffset + (size_t)img * G.planeBytes;
-  const uint8_t *centre = pyr + plane + (size_t)(s.y + kEdge) * G.pitch + (s.x + kEdge);
 
   // ---- every global load of this keypoint is issued up front (31 orientation rows + 13 patch words per lane), so a
   // warp pays one memory latency instead of one per row
@@ -132,32 +134,35 @@ k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, co
   const int u = lane - kHalfPatch;
   const int au = abs(u);
   int ring[2 * kHalfPatch + 1];
+  {
+    const uint8_t *rp = pyr + plane + (size_t)(s.y + kEdge - kHalfPatch) * pitch + (s.x + kEdge + u);
 #pragma unroll
-  for (int i = 0; i <= 2 * kHalfPatch; i++) {
-    const int v = i - kHalfPatch;
-    ring[i] = (lane < 31 && au <= kUmax[v < 0 ? -v : v]) ? (int)centre[v * G.pitch + u] : 0;
+    for (int i = 0; i <= 2 * kHalfPatch; i++, rp += pitch) {
+      const int v = i - kHalfPatch;
+      ring[i] = (lane < 31 && au <= kUmax[v < 0 ? -v : v]) ? (int)*rp : 0;
+    }
   }
-  // blurred patch: rows y-18 .. y+18, from the 4-byte aligned column at or before x-18
+  // blurred patch: rows y-18 .. y+18, from the 4-byte aligned column at or before x-18; a warp-wide load covers 3 rows
   unsigned *patch = sPatch[threadIdx.x >> 5];
   const int px0 = s.x + kEdge - kPatchR;                       // padded column of the patch's first pixel
   const int lead = px0 & 3;
-  const uint8_t *src = blur + plane + (size_t)(s.y + kEdge - kPatchR) * G.pitch + (px0 - lead);
-  constexpr int kPatchIters = (kPatchRows * kPatchWords + 31) / 32;
+  const int sub = lane / kPatchWords, word = lane - sub * kPatchWords;   // lanes 30, 31 idle
   unsigned pw[kPatchIters];
+  {
+    const uint8_t *pp = blur + plane + (size_t)(s.y + kEdge - kPatchR + sub) * pitch + (px0 - lead) + 4 * word;
 #pragma unroll
-  for (int k = 0; k < kPatchIters; k++) {
-    const int i = lane + 32 * k;
-    const int r = i / kPatchWords, j = i - r * kPatchWords;
-    pw[k] = i < kPatchRows * kPatchWords ? *reinterpret_cast<const unsigned *>(src + (size_t)r * G.pitch + 4 * j) : 0u;
+    for (int k = 0; k < kPatchIters; k++, pp += 3 * pitch)
+      pw[k] = (sub < 3 && 3 * k + sub < kPatchRows) ? *reinterpret_cast<const unsigned *>(pp) : 0u;
   }
 
   // ---- IC_Angle
   int m10 = 0, m01 = 0;
 #pragma unroll
   for (int i = 0; i <= 2 * kHalfPatch; i++) {
-    m10 += u * ring[i];
+    m10 += ring[i];
     m01 += (i - kHalfPatch) * ring[i];
   }
+  m10 *= u;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     m10 += __shfl_xor_sync(0xffffffffu, m10, o);
@@ -165,32 +170,30 @@ k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, co
   }
   const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-  // ---- steered BRIEF on the blurred level
+  // ---- steered BRIEF on the staged blurred patch
   const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
   float a, b;
   sincos_glibc(__fmul_rn(angle, factorPI), &b, &a);   // a = cos, b = sin
 #pragma unroll
-  for (int k = 0; k < kPatchIters; k++) {
-    const int i = lane + 32 * k;
-    if (i < kPatchRows * kPatchWords) patch[i] = pw[k];
-  }
+  for (int k = 0; k < kPatchIters; k++)
+    if (sub < 3 && 3 * k + sub < kPatchRows) patch[(3 * k + sub) * kPatchWords + word] = pw[k];
   __syncwarp();
   const uint8_t *bc = reinterpret_cast<const uint8_t *>(patch) + kPatchR * (kPatchWords * 4) + lead + kPatchR;
-  const signed char *p = sPat + lane * 32;     // 16 pattern points (x, y) per descriptor byte
+  const float2 *p = sPat + lane * 16;          // 16 pattern points (x, y) per descriptor byte
   unsigned val = 0;
 #pragma unroll
-  for (int bit = 0; bit < 8; bit++, p += 4) {
+  for (int bit = 0; bit < 8; bit++) {
     int t[2];
 #pragma unroll
     for (int e = 0; e < 2; e++) {
-      const float px = (float)p[2 * e], py = (float)p[2 * e + 1];
-      const int ry = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
-      const int rx = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+      const float2 q = p[2 * bit + e];
+      const int ry = __float2int_rn(__fadd_rn(__fmul_rn(q.x, b), __fmul_rn(q.y, a)));
+      const int rx = __float2int_rn(__fsub_rn(__fmul_rn(q.x, a), __fmul_rn(q.y, b)));
       t[e] = bc[ry * (kPatchWords * 4) + rx];
     }
     val |= (unsigned)(t[0] < t[1]) << bit;
   }
-  const size_t row = (size_t)img * kpCap + start + k;
+  const size_t row = (size_t)img * kpCap + slot;
   desc[row * 32 + lane] = (uint8_t)val;
   if (lane == 0) {
     orbgpu_keypoint o;
@@ -207,12 +210,10 @@ k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, co
 
 }  // namespace
 
-cudaError_t launch_describe(const LevelTable &T, const ExtractBuffers &B, int batch, cudaStream_t s) {
-  int maxSel = 1;
-  for (int l = 0; l < T.nlevels; l++) maxSel = max(maxSel, T.lv[l].selCap);
-  dim3 grid((maxSel + kWarpsPerCta - 1) / kWarpsPerCta, T.nlevels, batch);
+cudaError_t launch_describe(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, cudaStream_t s) {
+  dim3 grid((T.kpCap + kWarpsPerCta - 1) / kWarpsPerCta, batch);
   k_describe<<<grid, kWarpsPerCta * 32, 0, s>>>(B.dT, B.pyr, B.blur, B.sel, B.selCount, B.kps, B.desc, B.kpCount,
-                                                B.status);
+                                                B.status, imgBase);
   count_launch();
   return cudaGetLastError();
 }

@@ -51,16 +51,14 @@ __device__ __forceinline__ unsigned pair_at(unsigned w0, unsigned w1, unsigned w
 }
 
 // Arc margins (packed s16x2) of the two pixels at window bytes C, C+1; rows[r] = window words of image row y-3+r.
-// Differences are kept biased, d' = ring - centre + 256 in [1, 511] per half: both halves stay positive, so the 32
-// subtractions are plain 32-bit multiply-adds (FMA pipe) with no carry between halves, leaving the half-rate ALU
-// pipe to the 160 packed min/max; the bias is removed from the two arc extrema at the end.
+// min / max commute with subtracting the centre, so the sliding-window networks run on the RAW ring pixels and the
+// centre is subtracted once from the two extrema:
+//   bright margin = max_arcs min_arc(ring) - centre ,  dark margin = centre - min_arcs max_arc(ring).
 template <int C>
 __device__ __forceinline__ unsigned margin_pair(const unsigned (&w)[7][3]) {
-  const unsigned bias = 0x01000100u - pair_at<C>(w[3][0], w[3][1], w[3][2]);   // 256 - centre per half, no borrow
-  const unsigned one = 1u;
   unsigned d[16];
   // ring order of cv::FAST 9/16: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
-#define RING(k, dx, dy) d[k] = pair_at<C + (dx)>(w[3 + (dy)][0], w[3 + (dy)][1], w[3 + (dy)][2]) * one + bias
+#define RING(k, dx, dy) d[k] = pair_at<C + (dx)>(w[3 + (dy)][0], w[3 + (dy)][1], w[3 + (dy)][2])
   RING(0, 0, 3);   RING(1, 1, 3);   RING(2, 2, 2);    RING(3, 3, 1);
   RING(4, 3, 0);   RING(5, 3, -1);  RING(6, 2, -2);   RING(7, 1, -3);
   RING(8, 0, -3);  RING(9, -1, -3); RING(10, -2, -2); RING(11, -3, -1);
@@ -72,7 +70,7 @@ __device__ __forceinline__ unsigned margin_pair(const unsigned (&w)[7][3]) {
     a3[k] = mn3(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
     b3[k] = mx3(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
   }
-  unsigned bright = 0u, darkNeg = 0x7fff7fffu;
+  unsigned bright = 0u, dark = 0x7fff7fffu;
 #pragma unroll
   for (int k = 0; k < 16; k += 2) {
     const unsigned a9 = mn3(a3[k], a3[(k + 3) & 15], a3[(k + 6) & 15]);
@@ -80,20 +78,20 @@ __device__ __forceinline__ unsigned margin_pair(const unsigned (&w)[7][3]) {
     bright = mx3(bright, a9, a9b);
     const unsigned b9 = mx3(b3[k], b3[(k + 3) & 15], b3[(k + 6) & 15]);
     const unsigned b9b = mx3(b3[k + 1], b3[(k + 4) & 15], b3[(k + 7) & 15]);
-    darkNeg = mn3(darkNeg, b9, b9b);
+    dark = mn3(dark, b9, b9b);
   }
-  // bright margin = bright - 256, dark margin = 256 - darkNeg  (each within [-255, 255])
-  return mx2(__vsub2(bright, 0x01000100u), __vsub2(0x01000100u, darkNeg));
+  const unsigned c = pair_at<C>(w[3][0], w[3][1], w[3][2]);
+  return mx2(__vsub2(bright, c), __vsub2(c, dark));
 }
 
 // Geometry of one work item = one tile of one image.
 struct TileGeom {
   int level, img, X0, Y0, TW, TH, gx0, offL, groups, bx, lead;
 };
-__device__ __forceinline__ TileGeom tile_geom(const LevelTable *T, const int4 *tiles, int ntiles, int item) {
+__device__ __forceinline__ TileGeom tile_geom(const LevelTable *T, const int4 *tiles, int ntiles, int item, int imgBase) {
   TileGeom t;
   const int ti = item % ntiles;
-  t.img = item / ntiles;
+  t.img = imgBase + item / ntiles;
   const int4 tile = tiles[ti];                            // (level, cell row i, first cell column j0, cell count)
   t.level = tile.x;
   const LevelGeom &G = T->lv[t.level];
@@ -115,7 +113,7 @@ __device__ __forceinline__ TileGeom tile_geom(const LevelTable *T, const int4 *t
 // copy of the next tile is in flight while the current one is processed.
 __global__ void __launch_bounds__(kThreads, 4)
 k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict__ T, const int4 *__restrict__ tiles,
-             int ntiles, int totalItems, Cand *__restrict__ cand, int *__restrict__ candCount,
+             int ntiles, int totalItems, int imgBase, Cand *__restrict__ cand, int *__restrict__ candCount,
              unsigned *__restrict__ status, const FastConfig cfg) {
   extern __shared__ uint8_t smemRaw[];
   __shared__ __align__(8) unsigned long long sBar[2];
@@ -137,7 +135,7 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
   }
   __syncthreads();
   if (tid == 0 && (int)blockIdx.x < totalItems) {
-    const TileGeom n = tile_geom(T, tiles, ntiles, blockIdx.x);
+    const TileGeom n = tile_geom(T, tiles, ntiles, blockIdx.x, imgBase);
     const LevelGeom &Gn = T->lv[n.level];
     mbar_expect_tx(&sBar[0], (unsigned)(Gn.fastBoxW * Gn.fastBoxH));
     tma_load_3d(smem, &maps.m[n.level], n.bx, n.Y0 - 3 + kEdge, n.img, &sBar[0]);
@@ -146,7 +144,7 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
   int iter = 0;
   for (int item = blockIdx.x; item < totalItems; item += gridDim.x, iter++) {
     const int stage = iter & 1;
-    const TileGeom tg = tile_geom(T, tiles, ntiles, item);
+    const TileGeom tg = tile_geom(T, tiles, ntiles, item, imgBase);
     const LevelGeom &G = T->lv[tg.level];
     const int level = tg.level, img = tg.img, X0 = tg.X0, Y0 = tg.Y0, TW = tg.TW, TH = tg.TH;
     const int offL = tg.offL, groups = tg.groups, lead = tg.lead;
@@ -156,7 +154,7 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
       sEmit = 0; sQueued = 0; sKept = 0; sOut = 0;
       const int next = item + gridDim.x;
       if (next < totalItems) {                            // the other stage was released by the barrier ending the last item
-        const TileGeom n = tile_geom(T, tiles, ntiles, next);
+        const TileGeom n = tile_geom(T, tiles, ntiles, next, imgBase);
         const LevelGeom &Gn = T->lv[n.level];
         mbar_expect_tx(&sBar[stage ^ 1], (unsigned)(Gn.fastBoxW * Gn.fastBoxH));
         tma_load_3d(smem + (stage ^ 1) * cfg.imgBytes, &maps.m[n.level], n.bx, n.Y0 - 3 + kEdge, n.img, &sBar[stage ^ 1]);
@@ -294,13 +292,13 @@ FastConfig fast_make_config(const LevelTable &T) {
 }
 
 cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &maps, const int4 *tiles, int ntiles,
-                        const FastConfig &c, int batch, cudaStream_t s) {
+                        const FastConfig &c, int imgBase, int batch, cudaStream_t s) {
   const int total = ntiles * batch;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = total < 4 * sms ? total : 4 * sms;
-  k_fast_cells<<<grid, kThreads, c.smemBytes, s>>>(maps, B.dT, tiles, ntiles, total, B.cand, B.candCount, B.status, c);
+  k_fast_cells<<<grid, kThreads, c.smemBytes, s>>>(maps, B.dT, tiles, ntiles, total, imgBase, B.cand, B.candCount, B.status, c);
   count_launch();
   return cudaGetLastError();
 }

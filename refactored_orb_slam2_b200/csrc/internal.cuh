@@ -101,18 +101,18 @@ struct ExtractBuffers {
 };
 
 cudaError_t launch_import_level0(const LevelTable &T, const ExtractBuffers &B, const uint8_t *src,
-                                 size_t rowStep, size_t imgStep, int batch, cudaStream_t s);
-cudaError_t launch_resize_level(const LevelTable &T, const ExtractBuffers &B, int level, int batch,
+                                 size_t rowStep, size_t imgStep, int imgBase, int batch, cudaStream_t s);
+cudaError_t launch_resize_level(const LevelTable &T, const ExtractBuffers &B, int level, int imgBase, int batch,
                                 cudaStream_t s);
 void resize_box(const LevelTable &T, int l, int *boxW, int *boxH);
 int resize_smem_bytes(const LevelTable &T);
 cudaError_t resize_configure(int slotBytes);
 void resize_make_tiles(const LevelTable &T, int level, std::vector<int4> &tiles);
 cudaError_t launch_resize_tiles(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &maps, const int4 *tiles,
-                                int ntiles, int slotBytes, int batch, cudaStream_t s);
-cudaError_t launch_fill_borders(const LevelTable &T, const ExtractBuffers &B, int firstLevel, int batch, cudaStream_t s);
+                                int ntiles, int slotBytes, int imgBase, int batch, cudaStream_t s);
+cudaError_t launch_fill_borders(const LevelTable &T, const ExtractBuffers &B, int firstLevel, int imgBase, int batch, cudaStream_t s);
 cudaError_t launch_blur(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &maps, const int4 *tiles, int ntiles,
-                        int batch, cudaStream_t s);
+                        int imgBase, int batch, cudaStream_t s);
 int blur_box_w();
 int blur_box_h();
 int blur_smem_bytes();
@@ -122,11 +122,11 @@ constexpr int kFastCellsPerTile = 4;
 struct FastConfig { int imgBytes, scorePitch, scoreBytes, stageCap, queueCap, smemBytes, maxIters; };
 FastConfig fast_make_config(const LevelTable &T);
 cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &maps, const int4 *tiles, int ntiles,
-                        const FastConfig &c, int batch, cudaStream_t s);
-cudaError_t launch_octree(const LevelTable &T, const ExtractBuffers &B, int batch, int smemBytes,
+                        const FastConfig &c, int imgBase, int batch, cudaStream_t s);
+cudaError_t launch_octree(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, int smemBytes,
                           cudaStream_t s);
 int hamming_dense_q(int nq);
-cudaError_t launch_describe(const LevelTable &T, const ExtractBuffers &B, int batch, cudaStream_t s);
+cudaError_t launch_describe(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, cudaStream_t s);
 size_t octree_smem_bytes(int maxNodes);
 cudaError_t octree_configure(int smemBytes);
 cudaError_t fast_configure(int smemBytes);

@@ -109,13 +109,13 @@ __device__ __forceinline__ int nonempty_before(const int4 c, int q) {
 __global__ void __launch_bounds__(kThreads)
 k_octree(const LevelTable *__restrict__ T, const Cand *__restrict__ candAll, const int *__restrict__ candCount,
          unsigned short *__restrict__ nodeOfAll, int4 *__restrict__ selAll, int *__restrict__ selCount,
-         unsigned *__restrict__ status, int M, int M2) {
+         unsigned *__restrict__ status, int M, int M2, int imgBase) {
   extern __shared__ __align__(16) uint8_t smemRaw[];
   __shared__ int sTmp[kWarps + 2];
   __shared__ int sRootCnt[kMaxRoots], sRootPos[kMaxRoots];
   __shared__ int sSize, sNProc, sExpand;
 
-  const int level = blockIdx.x, img = blockIdx.y;
+  const int level = blockIdx.x, img = imgBase + blockIdx.y;
   const LevelGeom &G = T->lv[level];
   const int tid = threadIdx.x;
   const int N = G.quota;
@@ -350,14 +350,14 @@ cudaError_t octree_configure(int smemBytes) {
   return cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
 }
 
-cudaError_t launch_octree(const LevelTable &T, const ExtractBuffers &B, int batch, int smemBytes,
+cudaError_t launch_octree(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, int smemBytes,
                           cudaStream_t s) {
   int M = 0;
   for (int l = 0; l < T.nlevels; l++) M = max(M, T.lv[l].maxNodes);
   int M2 = 1;
   while (M2 < M) M2 <<= 1;
   dim3 grid(T.nlevels, batch);
-  k_octree<<<grid, kThreads, smemBytes, s>>>(B.dT, B.cand, B.candCount, B.nodeOf, B.sel, B.selCount, B.status, M, M2);
+  k_octree<<<grid, kThreads, smemBytes, s>>>(B.dT, B.cand, B.candCount, B.nodeOf, B.sel, B.selCount, B.status, M, M2, imgBase);
   count_launch();
   return cudaGetLastError();
 }

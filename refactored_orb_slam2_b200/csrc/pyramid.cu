@@ -27,9 +27,9 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 
 __global__ void __launch_bounds__(256)
 k_import_level0(const LevelTable *__restrict__ T, uint8_t *__restrict__ pyr, const uint8_t *__restrict__ src,
-                size_t rowStep, size_t imgStep) {
+                size_t rowStep, size_t imgStep, int imgBase) {
   const LevelGeom &G = T->lv[0];
-  const int img = blockIdx.z;
+  const int img = imgBase + blockIdx.z;
   const int py = blockIdx.y * blockDim.y + threadIdx.y;
   const int px4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (py >= G.rows || px4 >= G.pitch) return;
@@ -48,10 +48,10 @@ k_import_level0(const LevelTable *__restrict__ T, uint8_t *__restrict__ pyr, con
 
 __global__ void __launch_bounds__(256)
 k_resize_level(const LevelTable *__restrict__ T, uint8_t *__restrict__ pyr, const int2 *__restrict__ tabs,
-               int level) {
+               int level, int imgBase) {
   const LevelGeom &G = T->lv[level];
   const LevelGeom &P = T->lv[level - 1];
-  const int img = blockIdx.z;
+  const int img = imgBase + blockIdx.z;
   const int py = blockIdx.y * blockDim.y + threadIdx.y;
   const int px4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (py >= G.rows || px4 >= G.pitch) return;
@@ -89,7 +89,7 @@ constexpr int kRW = 128, kRH = 32, kResizeWarps = 4;
 
 __global__ void __launch_bounds__(kResizeWarps * 32)
 k_resize_tiles(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict__ T, const int2 *__restrict__ tabs,
-               const int4 *__restrict__ tiles, int ntiles, uint8_t *__restrict__ pyr, int slotBytes) {
+               const int4 *__restrict__ tiles, int ntiles, uint8_t *__restrict__ pyr, int slotBytes, int imgBase) {
   extern __shared__ uint8_t smemRaw[];
   __shared__ __align__(8) unsigned long long sBar[kResizeWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -98,8 +98,7 @@ k_resize_tiles(const __grid_constant__ TmaMaps maps, const LevelTable *__restric
   const int4 tile = tiles[t];                    // (level, tile x, tile y, 0)
   const int level = tile.x;
   const LevelGeom &G = T->lv[level];
-  const LevelGeom &P = T->lv[level - 1];
-  const int img = blockIdx.y;
+  const int img = imgBase + blockIdx.y;
   const int xp0 = 16 + kRW * tile.y;             // padded column of the tile's first output pixel (4-byte aligned)
   const int y0 = kRH * tile.z;                   // interior row of the tile's first output row
   const int xiFirst = min(max(xp0 - kEdge, 0), G.w - 1);
@@ -162,8 +161,8 @@ k_resize_tiles(const __grid_constant__ TmaMaps maps, const LevelTable *__restric
 // BORDER_REFLECT_101 apron of levels firstLevel .. nlevels-1 (ORBextractor.cc:1057-1059), one 32-bit word per item:
 // the 19 rows above / below the interior in full, and on interior rows the words covering the left and right aprons.
 __global__ void __launch_bounds__(256)
-k_fill_borders(const LevelTable *__restrict__ T, uint8_t *__restrict__ pyr, int firstLevel) {
-  const int level = firstLevel + blockIdx.y, img = blockIdx.z;
+k_fill_borders(const LevelTable *__restrict__ T, uint8_t *__restrict__ pyr, int firstLevel, int imgBase) {
+  const int level = firstLevel + blockIdx.y, img = imgBase + blockIdx.z;
   const LevelGeom &G = T->lv[level];
   uint8_t *plane = pyr + G.pyrOffset + (size_t)img * G.planeBytes;
   const int wordsPerRow = G.pitch >> 2;
@@ -200,17 +199,17 @@ static dim3 plane_grid(const LevelGeom &G, int batch, dim3 block) {
 }
 
 cudaError_t launch_import_level0(const LevelTable &T, const ExtractBuffers &B, const uint8_t *src,
-                                 size_t rowStep, size_t imgStep, int batch, cudaStream_t s) {
+                                 size_t rowStep, size_t imgStep, int imgBase, int batch, cudaStream_t s) {
   dim3 block(64, 4);
-  k_import_level0<<<plane_grid(T.lv[0], batch, block), block, 0, s>>>(B.dT, B.pyr, src, rowStep, imgStep);
+  k_import_level0<<<plane_grid(T.lv[0], batch, block), block, 0, s>>>(B.dT, B.pyr, src, rowStep, imgStep, imgBase);
   count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_resize_level(const LevelTable &T, const ExtractBuffers &B, int level, int batch,
+cudaError_t launch_resize_level(const LevelTable &T, const ExtractBuffers &B, int level, int imgBase, int batch,
                                 cudaStream_t s) {
   dim3 block(64, 4);
-  k_resize_level<<<plane_grid(T.lv[level], batch, block), block, 0, s>>>(B.dT, B.pyr, B.tabs, level);
+  k_resize_level<<<plane_grid(T.lv[level], batch, block), block, 0, s>>>(B.dT, B.pyr, B.tabs, level, imgBase);
   count_launch();
   return cudaGetLastError();
 }
@@ -243,17 +242,17 @@ void resize_make_tiles(const LevelTable &T, int level, std::vector<int4> &tiles)
 }
 
 cudaError_t launch_resize_tiles(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &maps, const int4 *tiles,
-                                int ntiles, int slotBytes, int batch, cudaStream_t s) {
+                                int ntiles, int slotBytes, int imgBase, int batch, cudaStream_t s) {
   dim3 grid((ntiles + kResizeWarps - 1) / kResizeWarps, batch);
-  k_resize_tiles<<<grid, kResizeWarps * 32, 128 + kResizeWarps * slotBytes, s>>>(maps, B.dT, B.tabs, tiles, ntiles, B.pyr, slotBytes);
+  k_resize_tiles<<<grid, kResizeWarps * 32, 128 + kResizeWarps * slotBytes, s>>>(maps, B.dT, B.tabs, tiles, ntiles, B.pyr, slotBytes, imgBase);
   count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_fill_borders(const LevelTable &T, const ExtractBuffers &B, int firstLevel, int batch, cudaStream_t s) {
+cudaError_t launch_fill_borders(const LevelTable &T, const ExtractBuffers &B, int firstLevel, int imgBase, int batch, cudaStream_t s) {
   if (firstLevel >= T.nlevels) return cudaSuccess;
   dim3 grid(8, T.nlevels - firstLevel, batch);
-  k_fill_borders<<<grid, 256, 0, s>>>(B.dT, B.pyr, firstLevel);
+  k_fill_borders<<<grid, 256, 0, s>>>(B.dT, B.pyr, firstLevel, imgBase);
   count_launch();
   return cudaGetLastError();
 }

@@ -15,13 +15,20 @@
 // published fixed-point algorithms and pinned bit-exact against cv2 4.13.0 by
 // tests/test_oracle_vs_cv2.py.
 //
-// PARITY UNPINNED at the reference level: the reference ships no tests, golden
-// vectors or fixtures for this path and cannot be compiled here (needs OpenCV
-// C++, Eigen, Pangolin).  What IS pinned: every OpenCV primitive vs real cv2,
-// the whole extractor vs an independent cv2-driven Python restatement
-// (oracle/oracle_cv2.py) and, when /root/reference is present, vs the
-// reference's own unmodified ORBextractor.cc compiled against an OpenCV API
-// shim (oracle/ref_shim, output oracle/_ref/).
+// PINNING.  The reference ships no tests, golden vectors or fixtures for this
+// path and its build (CMake + OpenCV C++, Eigen, Pangolin) is not possible
+// here.  The oracle is pinned three ways instead:
+//  1. every OpenCV primitive bit-exact vs real cv2 4.13.0;
+//  2. the whole extractor vs an independent cv2-driven Python restatement
+//     (oracle/oracle_cv2.py) and the golden vectors it produced (tests/golden);
+//  3. the whole extractor vs OUTPUTS OF THE REFERENCE ITSELF RUN HERE: its own,
+//     unmodified ORBextractor.cc compiled from /root/reference against an
+//     OpenCV API stand-in (oracle/ref_shim -> oracle/_ref/libref_orb.so;
+//     primitives = the restatements of (1), monotone allocator) — keypoints,
+//     order and descriptors byte-identical (tests/test_ref_vs_oracle.py).
+// ORBmatcher.cc / Frame.cc pull in the whole SLAM object graph and cannot be
+// built that way: DescriptorDistance, the best/second-best scan and
+// ComputeStereoMatches remain restatements (parity unpinned for those two).
 //
 // Two reference behaviours are not functions of the input and are fixed here
 // (see DESIGN.md "Determinisation"):
@@ -152,12 +159,15 @@ void fill_border(Plane &pl) {
 const int kGauss[7] = {18, 34, 48, 56, 48, 34, 18};
 void gaussian7_u8(const uint8_t *src, int w, int h, int sstride, uint8_t *dst, int dstride) {
   std::vector<uint16_t> tmp((size_t)w * h);
+  std::vector<uint8_t> line(w + 6);
   for (int y = 0; y < h; y++) {
     const uint8_t *S = src + (size_t)y * sstride;
+    for (int k = 0; k < 3; k++) { line[k] = S[reflect101(k - 3, w)]; line[w + 3 + k] = S[reflect101(w + k, w)]; }
+    std::memcpy(&line[3], S, w);
+    uint16_t *T = &tmp[(size_t)y * w];
     for (int x = 0; x < w; x++) {
-      int acc = 0;
-      for (int k = -3; k <= 3; k++) acc += kGauss[k + 3] * S[reflect101(x + k, w)];
-      tmp[(size_t)y * w + x] = (uint16_t)acc;
+      const uint8_t *p = &line[x];
+      T[x] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
     }
   }
   for (int y = 0; y < h; y++) {
@@ -165,8 +175,7 @@ void gaussian7_u8(const uint8_t *src, int w, int h, int sstride, uint8_t *dst, i
     for (int k = -3; k <= 3; k++) R[k + 3] = &tmp[(size_t)reflect101(y + k, h) * w];
     uint8_t *D = dst + (size_t)y * dstride;
     for (int x = 0; x < w; x++) {
-      uint32_t acc = 0;
-      for (int k = 0; k < 7; k++) acc += (uint32_t)kGauss[k] * R[k][x];
+      const uint32_t acc = 18u * (R[0][x] + R[6][x]) + 34u * (R[1][x] + R[5][x]) + 48u * (R[2][x] + R[4][x]) + 56u * R[3][x];
       D[x] = (uint8_t)((acc + 0x8000u) >> 16);
     }
   }
@@ -583,17 +592,34 @@ inline void scan_top2(const uint8_t *q, const uint8_t *train, const int *cand, i
 
 // ---------------------------------------------------------------- stereo
 
+// Read-only view of one pyramid level (interior pointer + row stride) so that the stereo restatement can run on the
+// oracle's own planes or on the reference-built checker's cv::Mat pyramids (oracle/ref_shim).
+struct LevelView {
+  const uint8_t *p; int w, h, stride;
+  const uint8_t *px(int x, int y) const { return p + (size_t)y * stride + x; }
+};
+struct PyramidView {
+  std::vector<LevelView> lv;
+  std::vector<float> scale, invScale;
+};
+PyramidView view_of(const Extractor &e) {
+  PyramidView v;
+  for (int l = 0; l < e.nlevels; l++) v.lv.push_back({e.pyr[l].px(0, 0), e.pyr[l].w, e.pyr[l].h, e.pyr[l].stride});
+  v.scale = e.scale; v.invScale = e.invScale;
+  return v;
+}
+
 // Frame.cc:477-646
-int stereo_matches(const Extractor &EL, const Extractor &ER, const KeyPointRec *kL,
-                   const uint8_t *dL, int nL, const KeyPointRec *kR, const uint8_t *dR, int nR,
-                   float mbf, float mb, float *uRight, float *depth, int *bestDistOut) {
+int stereo_matches_views(const PyramidView &VL, const PyramidView &VR, const KeyPointRec *kL,
+                         const uint8_t *dL, int nL, const KeyPointRec *kR, const uint8_t *dR, int nR,
+                         float mbf, float mb, float *uRight, float *depth, int *bestDistOut) {
   for (int i = 0; i < nL; i++) { uRight[i] = -1.0f; depth[i] = -1.0f; if (bestDistOut) bestDistOut[i] = -1; }
   const int thOrbDist = (100 + 50) / 2;
-  const int nRows = EL.pyr[0].h;
+  const int nRows = VL.lv[0].h;
   std::vector<std::vector<int>> rowIdx(nRows);
   for (int iR = 0; iR < nR; iR++) {
     const float y = kR[iR].y;
-    const float r = 2.0f * EL.scale[kR[iR].octave];
+    const float r = 2.0f * VL.scale[kR[iR].octave];
     const int maxr = (int)std::ceil(y + r), minr = (int)std::floor(y - r);
     for (int yi = minr; yi <= maxr; yi++)
       if (yi >= 0 && yi < nRows) rowIdx[yi].push_back(iR);  // reference: unchecked index
@@ -621,10 +647,10 @@ int stereo_matches(const Extractor &EL, const Extractor &ER, const KeyPointRec *
     }
     if (bestDist >= thOrbDist) continue;
     const float uR0 = kR[bestR].x;
-    const float sf = EL.invScale[levelL];
+    const float sf = VL.invScale[levelL];
     const float suL = std::round(kp.x * sf), svL = std::round(kp.y * sf), suR0 = std::round(uR0 * sf);
     const int w = 5, Lw = 5;
-    const Plane &PL = EL.pyr[levelL], &PR = ER.pyr[levelL];
+    const LevelView &PL = VL.lv[levelL], &PR = VR.lv[levelL];
     const float iniu = suR0 + Lw - w, endu = suR0 + Lw + w + 1;
     if (iniu < 0 || endu >= PR.w) continue;
     const int cy = (int)svL, cxL = (int)suL, cxR = (int)suR0;
@@ -645,7 +671,7 @@ int stereo_matches(const Extractor &EL, const Extractor &ER, const KeyPointRec *
     const float d1 = dists[Lw + bestInc - 1], d2 = dists[Lw + bestInc], d3 = dists[Lw + bestInc + 1];
     const float deltaR = (d1 - d3) / (2.0f * (d1 + d3 - 2.0f * d2));
     if (deltaR < -1 || deltaR > 1) continue;
-    float bestuR = EL.scale[levelL] * ((float)suR0 + (float)bestInc + deltaR);
+    float bestuR = VL.scale[levelL] * ((float)suR0 + (float)bestInc + deltaR);
     float disparity = uL - bestuR;
     if (disparity >= minD && disparity < maxD) {
       if (disparity <= 0) { disparity = (float)0.01; bestuR = (float)(uL - 0.01); }
@@ -667,6 +693,12 @@ int stereo_matches(const Extractor &EL, const Extractor &ER, const KeyPointRec *
     kept--;
   }
   return kept;
+}
+
+int stereo_matches(const Extractor &EL, const Extractor &ER, const KeyPointRec *kL, const uint8_t *dL, int nL,
+                   const KeyPointRec *kR, const uint8_t *dR, int nR, float mbf, float mb, float *uRight, float *depth,
+                   int *bestDistOut) {
+  return stereo_matches_views(view_of(EL), view_of(ER), kL, dL, nL, kR, dR, nR, mbf, mb, uRight, depth, bestDistOut);
 }
 
 template <class F>
@@ -867,6 +899,21 @@ void orb_oracle_stereo_batch(int nfeatures, float scaleFactor, int nlevels, int 
                      : 0;
   });
   for (auto &c : ctx) { delete c.L; delete c.R; }
+}
+
+// Frame::ComputeStereoMatches on caller-provided pyramids: per level an interior pointer, width, height and row stride.
+int orb_oracle_stereo_views(int nlevels, const uint8_t *const *planesL, const uint8_t *const *planesR, const int *w, const int *h,
+                            const int *strideL, const int *strideR, const float *scale, const float *invScale, const void *kL,
+                            const uint8_t *dL, int nL, const void *kR, const uint8_t *dR, int nR, float mbf, float mb,
+                            float *uRight, float *depth) {
+  PyramidView VL, VR;
+  for (int l = 0; l < nlevels; l++) {
+    VL.lv.push_back({planesL[l], w[l], h[l], strideL[l]});
+    VR.lv.push_back({planesR[l], w[l], h[l], strideR[l]});
+  }
+  VL.scale.assign(scale, scale + nlevels); VL.invScale.assign(invScale, invScale + nlevels);
+  VR.scale = VL.scale; VR.invScale = VL.invScale;
+  return stereo_matches_views(VL, VR, (const KeyPointRec *)kL, dL, nL, (const KeyPointRec *)kR, dR, nR, mbf, mb, uRight, depth, nullptr);
 }
 
 }  // extern "C"

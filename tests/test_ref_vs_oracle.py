@@ -1,0 +1,57 @@
+"""The reference's OWN ORBextractor.cc (compiled from /root/reference against the OpenCV API stand-in of
+oracle/ref_shim, primitives = the cv2-pinned restatements, monotone allocator) against the oracle: keypoints
+(position, order, size, angle, response, octave) and descriptors must be byte-identical.  This is what pins
+the restated glue — cell loops, DivideNode / DistributeOctTree list discipline, IC_Angle, computeOrbDescriptor,
+operator() — to the reference's code itself.  CPU only; skipped where the checker can be neither found nor built."""
+import numpy as np
+import pytest
+
+import gen_synth
+import oracle
+import ref
+
+pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libref_orb.so absent and /root/reference not present")
+
+CASES = [(640, 480, 1000, 1, (1.2, 8, 20, 7)), (1241, 376, 2000, 2, (1.2, 8, 20, 7)), (752, 480, 1200, 1000, (1.2, 8, 20, 7)),
+         (333, 251, 300, 5, (1.2, 8, 20, 7)), (1241, 376, 2000, 12, (1.2, 8, 12, 7)), (640, 480, 800, 21, (1.5, 4, 25, 10)),
+         (400, 300, 4000, 8, (1.2, 8, 20, 7))]
+
+
+@pytest.mark.parametrize("w,h,nf,seed,rest", CASES)
+def test_reference_code_equals_oracle(w, h, nf, seed, rest):
+    img = gen_synth.texture(h, w, seed)
+    k, d = oracle.OracleExtractor(nf, *rest)(img)
+    r = ref.ReferenceExtractor(nf, *rest)
+    rk, rd = r(img)
+    assert len(rk) == len(k)
+    for f in k.dtype.names:
+        assert np.array_equal(rk[f], k[f]), f
+    assert np.array_equal(rd, d)
+
+
+def test_reference_pyramid_and_repeat_calls():
+    """Same handle, several frames (exercises the two-arena allocator), and mvImagePyramid bytes."""
+    r = ref.ReferenceExtractor(1000)
+    o = oracle.OracleExtractor(1000)
+    for seed in (3, 4, 5, 6):
+        img = gen_synth.texture(480, 640, seed)
+        rk, rd = r(img)
+        k, d = o(img)
+        assert np.array_equal(rd, d) and np.array_equal(rk["x"], k["x"]) and np.array_equal(rk["angle"], k["angle"])
+    for l in range(8):
+        assert np.array_equal(r.level(l), o.level(l, 0))
+
+
+def test_noise_image_many_ties():
+    img = np.random.default_rng(5).integers(0, 256, (251, 333), dtype=np.uint8)
+    k, d = oracle.OracleExtractor(300)(img)
+    rk, rd = ref.ReferenceExtractor(300)(img)
+    assert np.array_equal(rd, d) and np.array_equal(rk["x"], k["x"]) and np.array_equal(rk["y"], k["y"])
+
+
+def test_stereo_batch_threads_agree_with_oracle_counts():
+    left, right = gen_synth.frame_batch(6, 376, 1241, 50, stereo=True)
+    params = (2000, 1.2, 8, 20, 7)
+    cl, cr, m = ref.stereo_batch(params, left, right, 386.1448, np.float32(386.1448) / np.float32(718.856), 3)
+    ol, orr, om = oracle.stereo_batch(params, left, right, 386.1448, np.float32(np.float32(386.1448) / np.float32(718.856)), 3)
+    assert np.array_equal(cl, ol) and np.array_equal(cr, orr) and np.array_equal(m, om)

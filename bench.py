@@ -40,6 +40,11 @@ BYTES_PER_IMAGE = LEVEL_PIXELS + (LEVEL_PIXELS - W * H) + 60 * 2006
 HAMMING_NQ, HAMMING_BANK = 2000, 1_000_000   # BASELINE.json configs[3]
 
 
+def log(msg):
+    if os.environ.get("BENCH_VERBOSE"):
+        print("[bench rank %s] %s" % (os.environ.get("RANK", "0"), msg), file=sys.stderr, flush=True)
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -156,6 +161,10 @@ def run_own(args, rank, local_rank, world):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    # stdout carries exactly ONE JSON line: anything libraries print there (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -175,6 +184,7 @@ def run_own(args, rank, local_rank, world):
 
     pairs = args.pairs
     nimg = 2 * pairs
+    log("world %d local_rank %d: generating %d pairs" % (world, local_rank, pairs))
     host = torch.from_numpy(make_inputs(pairs, 100 + rank)).pin_memory()
     dev = host.cuda()
     mb = float(np.float32(np.float32(BF) / np.float32(FX)))
@@ -187,18 +197,23 @@ def run_own(args, rank, local_rank, world):
         ex.extract_batch_device(dev.data_ptr(), nimg, W, H)
         pkg._lib.check(lib.orbgpu_stereo_match_device(ex.handle, ex.handle, 0, pairs, pairs, BF, mb))
 
+    log("handle ready")
     # ---- device-resident throughput (`value`)
-    for _ in range(args.warmup):
-        step_device()
-    ex.synchronize()
-    ex.stage_times()                               # open a fresh averaging window for the per-stage timers
     visible = os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")
     smi_index = int(visible[local_rank]) if local_rank < len(visible) and visible[local_rank].strip().isdigit() else local_rank
     sampler = ClockSampler(smi_index)
+    if rank == 0:
+        sampler.start()                            # sampled from warm-up to the end of the e2e loop (the GPU is loaded throughout)
+    t_warm = time.perf_counter()
+    for _ in range(args.warmup):
+        step_device()
+    ex.synchronize()
+    while time.perf_counter() - t_warm < 0.5:      # keep the clocks up until the sampler has ticked a few times
+        step_device()
+        ex.synchronize()
+    ex.stage_times()                               # open a fresh averaging window for the per-stage timers
     lib.orbgpu_launch_count(1)
     barrier()
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -207,13 +222,12 @@ def run_own(args, rank, local_rank, world):
     barrier()
     launches = int(lib.orbgpu_launch_count(0))
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
     ex.synchronize()                               # raises if a device buffer overflowed
     stages = ex.stage_times()
     ms_step = ms_total / args.steps
     fps = world * nimg * args.steps / (ms_total * 1e-3)
 
-    counts = np.zeros(nimg, np.int32)
+    log("device loop done: %.3f ms/step" % ms_step)
     kps, desc, counts = ex.download_results()
     mean_kp = float(counts.mean())
 
@@ -242,10 +256,12 @@ def run_own(args, rank, local_rank, world):
     torch.cuda.synchronize()
     dt = max_over_ranks(time.perf_counter() - t0)
     e2e_fps = world * nimg * args.steps / dt
+    clocks = sampler.stop() if rank == 0 else None
     kmax = int(out_c.max())
     h2d = nimg * W * H
     d2h = nimg * 4 + nimg * kmax * (28 + 32) + 2 * pairs * cap * 4
 
+    log("e2e loop done")
     # ---- Hamming matching, BASELINE.json configs[3]: 2000 queries x 1M-row bank, row-sharded over the ranks,
     # all-gather of the per-shard {d1, d2, idx} records, merge + ratio test on every rank
     hamming = None
@@ -300,6 +316,7 @@ def run_own(args, rank, local_rank, world):
                                         "compression executes 4 POPC + 16 LOP3 per pair, so frac may exceed the naive bound",
                                 "popc_per_s_measured": popc.value, "lop3_per_s_measured": lop3.value}}
 
+    log("hamming done")
     if rank == 0:
         peaks = {}
         try:
@@ -349,7 +366,8 @@ def run_own(args, rank, local_rank, world):
             "cpu_baseline": cpu_baseline,
             "hamming": hamming,
         }
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -359,7 +377,7 @@ def run_own(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--pairs", type=int, default=160, help="stereo pairs per step per GPU (320 images = 149 MB > L2)")

@@ -76,37 +76,38 @@ k_blur(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict__ T, c
 #pragma unroll
     for (int p = 0; p < 4; p++) acc[j][p] = 0;
 
+  // 7 input rows per loop trip: the accumulator rotation has period 7, so registers stay static while the code stays
+  // small enough for the instruction cache (a full 70-row unroll stalled on instruction fetch)
+  static_assert(kBoxH % 7 == 0, "row loop is unrolled by the accumulator period");
+  for (int r0 = 0; r0 < kBoxH; r0 += 7) {
 #pragma unroll
-  for (int r = 0; r < kBoxH; r++) {
-    // horizontal taps of input row r (tile row r-3): h for pixels x..x+3, two pixels per register
-    const unsigned *row = reinterpret_cast<const unsigned *>(slot + r * kBoxW) + lane;
-    const unsigned w0 = row[0], w1 = row[1], w2 = row[2];
-    const unsigned p1 = pair_at<1>(w0, w1, w2), p2 = pair_at<2>(w0, w1, w2), p3 = pair_at<3>(w0, w1, w2),
-                   p4 = pair_at<4>(w0, w1, w2), p5 = pair_at<5>(w0, w1, w2), p6 = pair_at<6>(w0, w1, w2),
-                   p7 = pair_at<7>(w0, w1, w2), p8 = pair_at<8>(w0, w1, w2), p9 = pair_at<9>(w0, w1, w2);
-    // pixel pair (x, x+1): window bytes 1..8 ; pair (x+2, x+3): bytes 3..10
-    const unsigned hA = 18u * (p1 + p7) + 34u * (p2 + p6) + 48u * (p3 + p5) + 56u * p4;
-    const unsigned hB = 18u * (p3 + p9) + 34u * (p4 + p8) + 48u * (p5 + p7) + 56u * p6;
-    const unsigned h[4] = {hA & 0xffffu, hA >> 16, hB & 0xffffu, hB >> 16};
-    // vertical taps: input row r feeds output rows r-6 .. r (tile rows), weights 18,34,48,56,48,34,18
+    for (int rr = 0; rr < 7; rr++) {
+      const int r = r0 + rr;
+      // horizontal taps of input row r (tile row r-3): h for pixels x..x+3, two pixels per register
+      const unsigned *row = reinterpret_cast<const unsigned *>(slot + r * kBoxW) + lane;
+      const unsigned w0 = row[0], w1 = row[1], w2 = row[2];
+      const unsigned p1 = pair_at<1>(w0, w1, w2), p2 = pair_at<2>(w0, w1, w2), p3 = pair_at<3>(w0, w1, w2),
+                     p4 = pair_at<4>(w0, w1, w2), p5 = pair_at<5>(w0, w1, w2), p6 = pair_at<6>(w0, w1, w2),
+                     p7 = pair_at<7>(w0, w1, w2), p8 = pair_at<8>(w0, w1, w2), p9 = pair_at<9>(w0, w1, w2);
+      // pixel pair (x, x+1): window bytes 1..8 ; pair (x+2, x+3): bytes 3..10
+      const unsigned hA = 18u * (p1 + p7) + 34u * (p2 + p6) + 48u * (p3 + p5) + 56u * p4;
+      const unsigned hB = 18u * (p3 + p9) + 34u * (p4 + p8) + 48u * (p5 + p7) + 56u * p6;
+      const unsigned h[4] = {hA & 0xffffu, hA >> 16, hB & 0xffffu, hB >> 16};
+      // vertical taps: input row r feeds output rows r-6 .. r; accumulator (rr + j) % 7 belongs to output row r-6+j
+      constexpr unsigned kW[7] = {18u, 34u, 48u, 56u, 48u, 34u, 18u};
 #pragma unroll
-    for (int p = 0; p < 4; p++) {
-      acc[0][p] += 18u * h[p]; acc[1][p] += 34u * h[p]; acc[2][p] += 48u * h[p]; acc[3][p] += 56u * h[p];
-      acc[4][p] += 48u * h[p]; acc[5][p] += 34u * h[p]; acc[6][p] += 18u * h[p];
-    }
-    if (r >= 6) {
+      for (int j = 0; j < 7; j++)
+#pragma unroll
+        for (int p = 0; p < 4; p++) acc[(rr + j) % 7][p] += kW[6 - j] * h[p];
+      // accumulator rr now holds output row r-6 complete
       const int orow = r - 6;
-      if (colOk && orow < rowsOut) {
-        const unsigned out = ((acc[0][0] + 0x8000u) >> 16) | (((acc[0][1] + 0x8000u) >> 16) << 8) |
-                             (((acc[0][2] + 0x8000u) >> 16) << 16) | (((acc[0][3] + 0x8000u) >> 16) << 24);
+      if (orow >= 0 && colOk && orow < rowsOut) {
+        const unsigned out = ((acc[rr][0] + 0x8000u) >> 16) | (((acc[rr][1] + 0x8000u) >> 16) << 8) |
+                             (((acc[rr][2] + 0x8000u) >> 16) << 16) | (((acc[rr][3] + 0x8000u) >> 16) << 24);
         *reinterpret_cast<unsigned *>(dst + (size_t)orow * G.pitch) = out;
       }
-    }
-    // rotate: accumulator j+1 becomes j, a fresh one enters at the tail (static after unrolling)
 #pragma unroll
-    for (int p = 0; p < 4; p++) {
-      acc[0][p] = acc[1][p]; acc[1][p] = acc[2][p]; acc[2][p] = acc[3][p]; acc[3][p] = acc[4][p];
-      acc[4][p] = acc[5][p]; acc[5][p] = acc[6][p]; acc[6][p] = 0;
+      for (int p = 0; p < 4; p++) acc[rr][p] = 0;       // it restarts as the accumulator of output row r+1
     }
   }
 }

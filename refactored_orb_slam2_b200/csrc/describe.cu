@@ -13,6 +13,8 @@
 //    that cvRound(x*b + y*a) lands on the same pixel as on the host.
 //  * The keypoint record (cv::KeyPoint layout) and the 32-byte descriptor row go straight to their
 //    final, level-major slot: start = sum of the lower levels' octree counts.
+#include <mutex>
+
 #include "internal.cuh"
 
 namespace orbgpu {
@@ -22,6 +24,14 @@ namespace {
 __device__ const signed char d_pattern[1024] = {
 #include "../../include/orb_pattern.inc"
 };
+// The 512 pattern points as float2, transposed so that the 32 lanes of a warp (lane = descriptor byte) read
+// consecutive 8-byte entries: entry [j][lane] = point 16*lane + j.  Filled once per device by k_init_pattern; 4 KB,
+// L1-resident for the descriptor loop.
+__device__ float2 d_patternT[512];
+__global__ void k_init_pattern() {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 512) d_patternT[(i & 15) * 32 + (i >> 4)] = make_float2((float)d_pattern[2 * i], (float)d_pattern[2 * i + 1]);
+}
 
 // cv::fastAtan2(y, x) scalar path (called at ORBextractor.cc:99): degrees in [0, 360).
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
@@ -101,10 +111,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur,
            const int4 *__restrict__ selAll, const int *__restrict__ selCount, orbgpu_keypoint *__restrict__ kps,
            uint8_t *__restrict__ desc, int *__restrict__ kpCount, unsigned *__restrict__ status, int imgBase) {
-  __shared__ float2 sPat[512];
   __shared__ __align__(16) unsigned sPatch[kWarpsPerCta][kPatchRows * kPatchWords];
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) sPat[i] = make_float2((float)d_pattern[2 * i], (float)d_pattern[2 * i + 1]);
-  __syncthreads();
 
   const int img = imgBase + blockIdx.y;
   const int lane = threadIdx.x & 31;
@@ -179,14 +186,14 @@ k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, co
     if (sub < 3 && 3 * k + sub < kPatchRows) patch[(3 * k + sub) * kPatchWords + word] = pw[k];
   __syncwarp();
   const uint8_t *bc = reinterpret_cast<const uint8_t *>(patch) + kPatchR * (kPatchWords * 4) + lead + kPatchR;
-  const float2 *p = sPat + lane * 16;          // 16 pattern points (x, y) per descriptor byte
+  const float2 *p = d_patternT + lane;         // point 16*lane + j sits at p[32 * j]
   unsigned val = 0;
 #pragma unroll
   for (int bit = 0; bit < 8; bit++) {
     int t[2];
 #pragma unroll
     for (int e = 0; e < 2; e++) {
-      const float2 q = p[2 * bit + e];
+      const float2 q = __ldg(&p[32 * (2 * bit + e)]);
       const int ry = __float2int_rn(__fadd_rn(__fmul_rn(q.x, b), __fmul_rn(q.y, a)));
       const int rx = __float2int_rn(__fsub_rn(__fmul_rn(q.x, a), __fmul_rn(q.y, b)));
       t[e] = bc[ry * (kPatchWords * 4) + rx];
@@ -211,6 +218,20 @@ k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, co
 }  // namespace
 
 cudaError_t launch_describe(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, cudaStream_t s) {
+  static std::mutex mu;
+  static bool ready[64] = {};
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ready[dev & 63]) {
+      k_init_pattern<<<2, 256, 0, s>>>();
+      cudaError_t e = cudaGetLastError();
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // once per device: other handles' streams must see the table
+      if (e != cudaSuccess) return e;
+      ready[dev & 63] = true;
+    }
+  }
   dim3 grid((T.kpCap + kWarpsPerCta - 1) / kWarpsPerCta, batch);
   k_describe<<<grid, kWarpsPerCta * 32, 0, s>>>(B.dT, B.pyr, B.blur, B.sel, B.selCount, B.kps, B.desc, B.kpCount,
                                                 B.status, imgBase);

@@ -25,6 +25,8 @@
 // staged in shared memory and appended to the level's candidate list with one global atomic per CTA.
 // Candidate order in HBM is arbitrary: the octree only needs each candidate's position in the
 // reference's cell-major order to break response ties, and that is a function of (x, y).
+#include <cstdlib>
+
 #include "internal.cuh"
 #include "tma.cuh"
 
@@ -297,7 +299,8 @@ cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const TmaM
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = total < 4 * sms ? total : 4 * sms;
+  static const int ctasPerSm = [] { const char *e = getenv("ORBGPU_FAST_CTAS"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 4 ? v : 4; }();
+  const int grid = total < ctasPerSm * sms ? total : ctasPerSm * sms;
   k_fast_cells<<<grid, kThreads, c.smemBytes, s>>>(maps, B.dT, tiles, ntiles, total, imgBase, B.cand, B.candCount, B.status, c);
   count_launch();
   return cudaGetLastError();

@@ -17,12 +17,11 @@
 
 namespace orbgpu {
 
+// BORDER_REFLECT_101 index: -k -> k, n-1+k -> n-1-k.  Excursions are at most kEdge (19) beyond the interior and every
+// level is wider than that (the cell grid needs >= 62 pixels), so a single fold suffices.
 __device__ __forceinline__ int reflect101(int p, int n) {
-  // |p| excursions are at most kEdge (19) beyond the interior; a single fold suffices when n > 19,
-  // the loop covers tiny levels.
-  if (n == 1) return 0;
-  while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p;
-  return p;
+  p = p < 0 ? -p : p;
+  return p >= n ? 2 * (n - 1) - p : p;
 }
 
 __global__ void __launch_bounds__(256)
@@ -34,13 +33,19 @@ k_import_level0(const LevelTable *__restrict__ T, uint8_t *__restrict__ pyr, con
   const int px4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (py >= G.rows || px4 >= G.pitch) return;
   const uint8_t *S = src + (size_t)img * imgStep + (size_t)reflect101(py - kEdge, G.h) * rowStep;
-  unsigned out = 0;
+  unsigned out;
+  if (px4 >= kEdge && px4 + 3 < G.w + kEdge) {      // four interior pixels: no mirroring
+    const uint8_t *p = S + (px4 - kEdge);
+    out = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24);
+  } else {
+    out = 0;
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int px = px4 + k;
-    unsigned v = 0;
-    if (px < G.w + 2 * kEdge) v = S[reflect101(px - kEdge, G.w)];
-    out |= v << (8 * k);
+    for (int k = 0; k < 4; k++) {
+      const int px = px4 + k;
+      unsigned v = 0;
+      if (px < G.w + 2 * kEdge) v = S[reflect101(px - kEdge, G.w)];
+      out |= v << (8 * k);
+    }
   }
   uint8_t *D = pyr + G.pyrOffset + (size_t)img * G.planeBytes + (size_t)py * G.pitch + px4;
   *reinterpret_cast<unsigned *>(D) = out;

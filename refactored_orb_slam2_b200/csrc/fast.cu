@@ -125,8 +125,10 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
   const int iniTh = T->iniTh, minTh = T->minTh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint8_t *smem = smemRaw + ((128u - (smem_u32(smemRaw) & 127u)) & 127u);   // TMA destination: 128-byte aligned
-  uint8_t *sScore = smem + 2 * cfg.imgBytes;              // u8 scores, pitch cfg.scorePitch, column 0 = padded column gx0
-  Cand *sStage = reinterpret_cast<Cand *>(sScore + cfg.scoreBytes);
+  // u8 scores, pitch cfg.scorePitch, column 0 = padded column gx0; one halo row above / below (kept zero) and one halo
+  // column on each side (always masked by the cell test) so that NMS reads its 8 neighbours without bounds checks
+  uint8_t *sScore = smem + 2 * cfg.imgBytes + cfg.scorePitch + 4;
+  Cand *sStage = reinterpret_cast<Cand *>(smem + 2 * cfg.imgBytes + cfg.scoreBytes);
   unsigned short *sQueue = reinterpret_cast<unsigned short *>(sStage + cfg.stageCap);   // (row << 8 | column) of non-zero scores
   const int sp = cfg.scorePitch;
 
@@ -163,6 +165,11 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
       }
     }
     if (tid < kFastCellsPerTile) sCellCnt[tid] = 0;
+    for (int i = tid; i < 2 * (sp >> 2); i += kThreads) {   // zero the halo rows -1 and TH
+      const int half = sp >> 2;
+      unsigned *rowp = reinterpret_cast<unsigned *>(sScore + (i < half ? -1 : TH) * sp - 4);
+      rowp[i < half ? i : i - half] = 0u;
+    }
     __syncthreads();
     mbar_wait(&sBar[stage], (iter >> 1) & 1);
 
@@ -172,7 +179,6 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
     const int items = TH * groups;
     const int stepY = kThreads / groups, stepG = kThreads - stepY * groups;
     int y = tid / groups, g = tid - y * groups;
-    const unsigned ltMask = (1u << lane) - 1u;
     for (int i0 = 0; i0 < items; i0 += kThreads) {
       unsigned packed = 0;
       if (i0 + tid < items) {
@@ -192,19 +198,15 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
         if (hi < 4) packed &= 0xffffffffu >> (8 * (4 - hi));
         *reinterpret_cast<unsigned *>(sScore + y * sp + 4 * g) = packed;
       }
-      // queue the non-zero scores as (row << 8 | score column): one ballot per byte lane, one reservation per warp
-      if (__any_sync(0xffffffffu, packed != 0u)) {
-        const unsigned b0 = __ballot_sync(0xffffffffu, packed & 0xffu), b1 = __ballot_sync(0xffffffffu, packed & 0xff00u);
-        const unsigned b2 = __ballot_sync(0xffffffffu, packed & 0xff0000u), b3 = __ballot_sync(0xffffffffu, packed >> 24);
-        const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2);
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&sQueued, n0 + n1 + n2 + __popc(b3));
-        base = __shfl_sync(0xffffffffu, base, 0);
+      // queue the non-zero scores as (row << 8 | score column); one shared-memory reservation per lane that has any
+      if (packed != 0u) {
+        const int mine = (packed & 0xffu ? 1 : 0) + (packed & 0xff00u ? 1 : 0) + (packed & 0xff0000u ? 1 : 0) + (packed >> 24 ? 1 : 0);
+        int at = atomicAdd(&sQueued, mine);
         const unsigned short e = (unsigned short)((y << 8) | (4 * g));
-        if (packed & 0xffu) sQueue[base + __popc(b0 & ltMask)] = e;
-        if (packed & 0xff00u) sQueue[base + n0 + __popc(b1 & ltMask)] = e + 1;
-        if (packed & 0xff0000u) sQueue[base + n0 + n1 + __popc(b2 & ltMask)] = e + 2;
-        if (packed >> 24) sQueue[base + n0 + n1 + n2 + __popc(b3 & ltMask)] = e + 3;
+        if (packed & 0xffu) sQueue[at++] = e;
+        if (packed & 0xff00u) sQueue[at++] = e + 1;
+        if (packed & 0xff0000u) sQueue[at++] = e + 2;
+        if (packed >> 24) sQueue[at] = e + 3;
       }
       y += stepY; g += stepG;
       if (g >= groups) { g -= groups; y++; }
@@ -222,10 +224,12 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
     const int x = sx - offL;                               // tile coordinate
     const int c = (x >= G.wCell) + (x >= 2 * G.wCell) + (x >= 3 * G.wCell);
     const int cx0 = c * G.wCell, cx1 = min(cx0 + G.wCell, TW);
-    const bool left = x > cx0, right = x + 1 < cx1, up = y > 0, down = y + 1 < TH;
-    bool keep = (!left || s > c0[-1]) && (!right || s > c0[1]);
-    if (up) keep = keep && s > c0[-sp] && (!left || s > c0[-sp - 1]) && (!right || s > c0[-sp + 1]);
-    if (down) keep = keep && s > c0[sp] && (!left || s > c0[sp - 1]) && (!right || s > c0[sp + 1]);
+    // neighbours outside the cell's rectangle count as 0: rows -1 / TH are the zero halo, columns are masked
+    const bool left = x > cx0, right = x + 1 < cx1;
+    const int ml = max(max((int)c0[-1], (int)c0[-sp - 1]), (int)c0[sp - 1]);
+    const int mr = max(max((int)c0[1], (int)c0[-sp + 1]), (int)c0[sp + 1]);
+    const int m = max(max((int)c0[-sp], (int)c0[sp]), max(left ? ml : 0, right ? mr : 0));
+    const bool keep = s > m;
     if (keep) {
       const int slot = atomicAdd(&sKept, 1);
       if (slot < cfg.stageCap) {
@@ -285,7 +289,7 @@ FastConfig fast_make_config(const LevelTable &T) {
   const int tw = kFastCellsPerTile * wMax;
   c.imgBytes = (img + 127) & ~127;
   c.scorePitch = (tw + 3 + 3 + 3) & ~3;             // + the group overhang on both sides
-  c.scoreBytes = (c.scorePitch * hMax + 15) & ~15;
+  c.scoreBytes = (c.scorePitch * (hMax + 2) + 8 + 15) & ~15;   // + halo rows and the 4-byte lead of the halo column
   c.stageCap = (tw / 2 + 1) * (hMax / 2 + 1);      // bound on strict 8-neighbour maxima in a tile
   c.queueCap = c.scorePitch * hMax;
   c.smemBytes = 128 + 2 * c.imgBytes + c.scoreBytes + c.stageCap * (int)sizeof(Cand) + c.queueCap * 2;

@@ -328,9 +328,16 @@ def run_own(args, rank, local_rank, world):
         dom = max(("pyramid", "fast", "octree", "blur", "describe", "stereo"), key=lambda k: stages.get(k, 0.0))
         # algorithmic bytes of the dominant stage per launch: FAST reads every pyramid pixel once and writes 8 B per candidate;
         # the other stages' figures are listed in DESIGN.md
-        alg_bytes = {"fast": LEVEL_PIXELS, "pyramid": LEVEL_PIXELS + (LEVEL_PIXELS - W * H), "blur": 2 * LEVEL_PIXELS,
+        alg_bytes = {"fast": LEVEL_PIXELS + 8 * 27400, "pyramid": LEVEL_PIXELS + (LEVEL_PIXELS - W * H), "blur": 2 * LEVEL_PIXELS,
                      "octree": 8 * 27000, "describe": 60 * 2006 + 2006 * (749 + 512), "stereo": 2006 * (64 * 2000 // 32)}[dom] * nimg
         achieved = alg_bytes / (stages[dom] * 1e-3) / 1e9 if stages.get(dom) else 0.0
+        traffic = None      # dram__bytes_read + dram__bytes_write of the dominant kernel per launch, from the committed ncu capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_k_fast_cells_traffic.json")))
+            if dom == "fast":
+                traffic = int(tj["traffic_bytes_per_image"]) * nimg
+        except Exception:
+            pass
         pipeline_gbs = BYTES_PER_IMAGE * nimg / (ms_step * 1e-3) / 1e9
         cpu_baseline = None
         if not args.no_cpu_baseline:
@@ -359,7 +366,7 @@ def run_own(args, rank, local_rank, world):
             "stage_ms": stages,
             "roofline": {"bound": "hbm", "kernel": {"fast": "k_fast_cells", "pyramid": "k_resize_level", "octree": "k_octree", "blur": "k_blur_level",
                                                      "describe": "k_describe", "stereo": "k_stereo_match"}[dom],
-                         "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
+                         "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
                          "peak_source": peak_src,
                          "pipeline": {"achieved": pipeline_gbs, "frac": pipeline_gbs / peak_gbs,
                                       "bytes_per_image": BYTES_PER_IMAGE, "note": "SURVEY 8d per-image bytes x images / whole step time"}},

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -89,7 +90,7 @@ struct orbgpu_extractor {
   cudaEvent_t evDone = nullptr;
   int lastBatch = 0;
   // host-buffer pipeline: copy streams + per-chunk events
-  static constexpr int kMaxChunks = 4;
+  static constexpr int kMaxChunks = 16;
   cudaStream_t copyIn = nullptr, copyOut = nullptr;
   cudaEvent_t evChunkIn[kMaxChunks] = {}, evChunkDone[kMaxChunks] = {};
   // optional per-stage timing
@@ -606,7 +607,8 @@ int orbgpu_extract_batch(orbgpu_extractor *e, const uint8_t *images, int count, 
     for (auto &ev : e->evChunkDone) ORBGPU_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   }
   const size_t imgBytes = (size_t)width * height;
-  const int chunks = count >= 64 ? orbgpu_extractor::kMaxChunks : count >= 16 ? 2 : 1;
+  static const int wantChunks = [] { const char *v = getenv("ORBGPU_CHUNKS"); const int n = v ? atoi(v) : 4; return std::min(std::max(n, 1), (int)orbgpu_extractor::kMaxChunks); }();
+  const int chunks = count >= 8 * wantChunks ? wantChunks : count >= 16 ? 2 : 1;
   const int per = (count + chunks - 1) / chunks;
   const int cols = std::min(capacity, e->kpCap);
   begin_batch(e);

@@ -42,14 +42,23 @@ template <int VARIANT>
 __device__ __forceinline__ int distance256(const unsigned (&q)[8], const uint4 b0, const uint4 b1) {
   const unsigned x0 = q[0] ^ b0.x, x1 = q[1] ^ b0.y, x2 = q[2] ^ b0.z, x3 = q[3] ^ b0.w;
   const unsigned x4 = q[4] ^ b1.x, x5 = q[5] ^ b1.y, x6 = q[6] ^ b1.z, x7 = q[7] ^ b1.w;
-  if (VARIANT == 0) {
+  if (VARIANT == 0) {          // 8 POPC + 8 LOP3: the reference's arithmetic, POPC-bound (quarter-rate unit)
     return __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3) + __popc(x4) + __popc(x5) + __popc(x6) + __popc(x7);
-  } else {
+  } else if (VARIANT == 1) {   // 4 POPC + 16 LOP3: two levels of 3:2 compression, ALU-bound
     const unsigned s0 = lop3<0x96>(x0, x1, x2), c0 = lop3<0xe8>(x0, x1, x2);
     const unsigned s1 = lop3<0x96>(x3, x4, x5), c1 = lop3<0xe8>(x3, x4, x5);
     const unsigned s2 = lop3<0x96>(s0, s1, x6), c2 = lop3<0xe8>(s0, s1, x6);
     const unsigned s4 = lop3<0x96>(c0, c1, c2), c4 = lop3<0xe8>(c0, c1, c2);
     return __popc(s2) + __popc(x7) + 2 * __popc(s4) + 4 * __popc(c4);
+  } else if (VARIANT == 2) {   // 5 POPC + 14 LOP3: POPC (5/16 clk) and ALU (15/64 clk) nearly balanced
+    const unsigned s0 = lop3<0x96>(x0, x1, x2), c0 = lop3<0xe8>(x0, x1, x2);
+    const unsigned s1 = lop3<0x96>(x3, x4, x5), c1 = lop3<0xe8>(x3, x4, x5);
+    const unsigned s2 = lop3<0x96>(s0, s1, x6), c2 = lop3<0xe8>(s0, s1, x6);
+    return __popc(s2) + __popc(x7) + 2 * (__popc(c0) + __popc(c1) + __popc(c2));
+  } else {                     // 6 POPC + 12 LOP3
+    const unsigned s0 = lop3<0x96>(x0, x1, x2), c0 = lop3<0xe8>(x0, x1, x2);
+    const unsigned s1 = lop3<0x96>(x3, x4, x5), c1 = lop3<0xe8>(x3, x4, x5);
+    return __popc(s0) + __popc(s1) + __popc(x6) + __popc(x7) + 2 * (__popc(c0) + __popc(c1));
   }
 }
 
@@ -265,16 +274,18 @@ int hamming_dense_chunks(int rows, int nq, int smCount) {
 template <int Q>
 static void launch_dense_q(int variant, dim3 grid, cudaStream_t s, const uint8_t *bank, int rows, int chunkRows,
                            long long indexBase, const uint8_t *q, int nq, Top2Rec *partial) {
-  if (variant == 0)
-    k_hamming_dense<Q, 0><<<grid, kDenseThreads, 0, s>>>(bank, rows, chunkRows, indexBase, q, nq, partial);
-  else
-    k_hamming_dense<Q, 1><<<grid, kDenseThreads, 0, s>>>(bank, rows, chunkRows, indexBase, q, nq, partial);
+  switch (variant) {
+    case 0: k_hamming_dense<Q, 0><<<grid, kDenseThreads, 0, s>>>(bank, rows, chunkRows, indexBase, q, nq, partial); break;
+    case 1: k_hamming_dense<Q, 1><<<grid, kDenseThreads, 0, s>>>(bank, rows, chunkRows, indexBase, q, nq, partial); break;
+    case 3: k_hamming_dense<Q, 3><<<grid, kDenseThreads, 0, s>>>(bank, rows, chunkRows, indexBase, q, nq, partial); break;
+    default: k_hamming_dense<Q, 2><<<grid, kDenseThreads, 0, s>>>(bank, rows, chunkRows, indexBase, q, nq, partial); break;
+  }
 }
 
 cudaError_t launch_hamming_dense(const uint8_t *bank, int rows, long long indexBase, const uint8_t *q,
                                  int nq, Top2Rec *partial, int chunks, Top2Rec *result, cudaStream_t s) {
   if (nq <= 0) return cudaSuccess;
-  static const int variant = [] { const char *e = getenv("ORBGPU_HAMMING_VARIANT"); return e ? atoi(e) : 1; }();
+  static const int variant = [] { const char *e = getenv("ORBGPU_HAMMING_VARIANT"); return e ? atoi(e) : 2; }();
   if (rows > 0) {
     const int Q = hamming_dense_q(nq);
     const int chunkRows = (rows + chunks - 1) / chunks;

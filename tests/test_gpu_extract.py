@@ -100,6 +100,36 @@ def test_batch_equals_single_calls(pkg):
     assert np.array_equal(g.pyramid_level(3, image=5), o.level(3, 0))
 
 
+def test_chunked_host_pipeline_equals_single_calls(pkg):
+    """Batches of >= 32 images go through the 4-chunk H2D / kernels / D2H pipeline of orbgpu_extract_batch."""
+    imgs = gen_synth.frame_batch(37, 240, 416, 5)
+    params = (500, 1.2, 8, 20, 7)
+    g = pkg.ORBextractor(*params, max_width=416, max_height=240, max_batch=37)
+    kps, desc, counts = g.extract_batch(imgs)
+    o = oracle.OracleExtractor(*params)
+    for i in range(37):
+        ok, od = o(imgs[i])
+        assert counts[i] == len(ok), i
+        assert_same_keypoints(kps[i, :counts[i]], desc[i, :counts[i]], ok, od)
+    # the device-resident results of the same batch are what the host received
+    k2, d2, c2 = g.download_results()
+    assert np.array_equal(c2, counts) and np.array_equal(d2[5, :c2[5]], desc[5, :counts[5]])
+
+
+def test_stage_timers_and_pipe_probes(pkg):
+    import ctypes
+    g = pkg.ORBextractor(500, 1.2, 8, 20, 7, max_width=416, max_height=240, max_batch=4)
+    g.set_profiling(True)
+    g.extract_batch(gen_synth.frame_batch(4, 240, 416, 6))
+    t = g.stage_times()
+    assert set(t) == {"pyramid", "fast", "octree", "blur", "describe", "stereo"}
+    assert all(t[k] > 0 for k in ("pyramid", "fast", "octree", "blur", "describe")) and t["stereo"] == 0
+    popc, lop3 = ctypes.c_double(), ctypes.c_double()
+    pkg._lib.check(pkg.lib().orbgpu_measure_popc_peak(-1, ctypes.byref(popc), ctypes.byref(lop3)))
+    assert 1e12 < popc.value < 1e13 and 5e12 < lop3.value < 5e13      # 16 and 64 lanes/clk/SM on B200
+    assert pkg.lib().orbgpu_launch_count(0) > 0
+
+
 def test_handle_reuse_across_sizes_and_row_stride(pkg):
     params = (1000, 1.2, 8, 20, 7)
     g = pkg.ORBextractor(*params, max_width=800, max_height=600)

@@ -63,7 +63,7 @@ __device__ __forceinline__ int distance256(const unsigned (&q)[8], const uint4 b
 }
 
 template <int Q, int VARIANT>
-__global__ void __launch_bounds__(kDenseThreads)
+__global__ void __launch_bounds__(kDenseThreads, Q >= 8 ? 1 : 3)
 k_hamming_dense(const uint8_t *__restrict__ bank, int rows, int chunkRows, long long indexBase,
                 const uint8_t *__restrict__ queries, int nq, Top2Rec *__restrict__ partial) {
   __shared__ __align__(128) uint8_t sTile[kStages][kTileBytes];
@@ -261,7 +261,11 @@ __global__ void __launch_bounds__(256) k_pipe_probe(unsigned *out, int iters, un
 
 }  // namespace
 
-int hamming_dense_q(int nq) { return nq > 4 * kConsumers ? 8 : nq > 2 * kConsumers ? 4 : nq > kConsumers ? 2 : 1; }
+int hamming_dense_q(int nq) {
+  static const int forced = [] { const char *e = getenv("ORBGPU_HAMMING_Q"); return e ? atoi(e) : 0; }();
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
+  return nq > 4 * kConsumers ? 8 : nq > 2 * kConsumers ? 4 : nq > kConsumers ? 2 : 1;
+}
 
 int hamming_dense_chunks(int rows, int nq, int smCount) {
   const int Q = hamming_dense_q(nq);

@@ -65,3 +65,35 @@ def test_integer_shift_recovers_disparity(pkg):
     disp = f.mvKeys["x"][m] - f.mvuRight[m]
     assert abs(np.median(disp) - d) < 0.5
     assert np.allclose(f.mvDepth[m], np.float32(KITTI[0]) / disp, rtol=1e-6)
+
+
+def test_pipeline_equals_sequential_calls(pkg):
+    """StereoBatchPipeline (two handles, two host threads, batches in flight) returns exactly what sequential
+    extract_batch + ComputeStereoMatches calls return."""
+    npairs, params = 3, (1200, 1.2, 8, 20, 7)
+    bf, fx = EUROC
+    mb = float(np.float32(bf) / np.float32(fx))
+    batches = []
+    for seed in (1, 2, 3, 4, 5):
+        l, r = gen_synth.frame_batch(npairs, 480, 752, seed, stereo=True)
+        batches.append(np.ascontiguousarray(np.concatenate([l, r])))
+    pipe = pkg.StereoBatchPipeline(params, 752, 480, npairs, bf, mb, depth=2, pin_outputs=False)
+    g = pkg.ORBextractor(*params, max_width=752, max_height=480, max_batch=2 * npairs)
+    got = []
+    for i, b in enumerate(batches):
+        pipe.submit(b)
+        if i >= 1:
+            k, d, c, u, z = pipe.result()
+            got.append((k.copy(), d.copy(), c.copy(), u.copy(), z.copy()))
+    k, d, c, u, z = pipe.result()
+    got.append((k.copy(), d.copy(), c.copy(), u.copy(), z.copy()))
+    pipe.close()
+    for b, (k, d, c, u, z) in zip(batches, got):
+        k2, d2, c2 = g.extract_batch(b)
+        u2, z2 = pkg.ComputeStereoMatches(g, g, bf, mb, 0, npairs, npairs)
+        assert np.array_equal(c, c2)
+        for i in range(2 * npairs):
+            assert np.array_equal(d[i, :c[i]], d2[i, :c2[i]])
+            assert np.array_equal(k[i, :c[i]]["angle"], k2[i, :c2[i]]["angle"])
+        for i in range(npairs):
+            assert np.array_equal(u[i, :c[i]], u2[i, :c2[i]]) and np.array_equal(z[i, :c[i]], z2[i, :c2[i]])

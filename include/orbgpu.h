@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORBGPU_VERSION 100
+#define ORBGPU_VERSION 110
 
 enum {
   ORBGPU_OK = 0,
@@ -173,6 +173,118 @@ int orbgpu_top2_merge_device(const void *d_parts, int parts, int nq, void *d_res
 int orbgpu_hamming_top2_csr(const uint8_t *queries, int nq, const uint8_t *train, int nt,
                             const int32_t *offsets, const int32_t *cand, int32_t *idx1, int32_t *d1,
                             int32_t *d2, int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-resident feature sets and the ORBmatcher searches
+ *
+ * Every search of src/ORBmatcher.cc has the same shape: for each query (a projected MapPoint, a
+ * keypoint of another frame) enumerate candidate keypoints — the window walk of
+ * Frame::GetFeaturesInArea (src/Frame.cc:341-397) / KeyFrame::GetFeaturesInArea
+ * (src/KeyFrame.cc:526-567) over the 64x48 grid of Frame::AssignFeaturesToGrid (src/Frame.cc:250-263,
+ * 399-411), or the features of one vocabulary node — gate them, keep the best / second-best
+ * Hamming distance, accept by threshold and ratio, and in six of the eleven routines let an
+ * accepted match take its keypoint away from LATER queries.  One feature set = the undistorted
+ * keypoints, right coordinates, descriptors and grid of one Frame / KeyFrame, resident in HBM;
+ * orbgpu_search runs one whole routine's candidate loops on it.  What stays on the host (shim/
+ * ORBmatcher.cc) is what the reference computes per MapPoint BEFORE its candidate loop (projection,
+ * frustum and distance gates, PredictScale) and the pointer-graph updates AFTER it.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct orbgpu_features orbgpu_features;
+
+typedef struct orbgpu_features_desc {
+  int32_t n;                          /* Frame::N */
+  const orbgpu_keypoint *keys_un;     /* Frame::mvKeysUn (x, y, octave, angle are read) */
+  const float *u_right;               /* Frame::mvuRight, or NULL for "all -1" (monocular) */
+  const uint8_t *descriptors;         /* Frame::mDescriptors, [n][32] */
+  float min_x, min_y;                 /* Frame::mnMinX / mnMinY used by PosInGrid (src/Frame.cc:399-411) */
+  float grid_w_inv, grid_h_inv;       /* Frame::mfGridElementWidthInv / HeightInv */
+  int32_t grid_cols, grid_rows;       /* FRAME_GRID_COLS / ROWS (64 x 48, include/Frame.h:35-36) */
+  float query_min_x, query_min_y;     /* mnMinX / mnMinY as the window walk reads them: the same floats for a Frame,
+                                         the truncated ints of include/KeyFrame.h:190-193 for a KeyFrame */
+  int32_t device;                     /* CUDA device, -1 = current */
+} orbgpu_features_desc;
+
+/* Uploads one frame's features and builds its grid on the device (cell lists in ascending keypoint
+ * index, exactly the push_back order of AssignFeaturesToGrid). */
+int orbgpu_features_create(const orbgpu_features_desc *desc, orbgpu_features **out);
+/* The same from the device-resident output of the last extract_batch call on `e` (image `image`),
+ * device to device: keypoints and descriptors are taken from the extractor, u_right from the stereo
+ * results of orbgpu_stereo_match when `pair` >= 0 (else all -1).  Valid only for undistorted input
+ * (mDistCoef[0] == 0: Frame::UndistortKeyPoints copies mvKeys, src/Frame.cc:419-423). */
+int orbgpu_features_from_extractor(orbgpu_extractor *e, int image, int pair, const orbgpu_features_desc *geometry,
+                                   orbgpu_features **out);
+void orbgpu_features_destroy(orbgpu_features *f);
+int orbgpu_features_count(const orbgpu_features *f);
+/* Grid as CSR: cell (ix, iy) is row ix * grid_rows + iy (mGrid[ix][iy]); cell_start has cols*rows+1 entries,
+ * cell_items `n` entries (keypoints outside the grid appear in no cell; *n_items receives the number stored). */
+int orbgpu_features_grid(orbgpu_features *f, int32_t *cell_start, int32_t *cell_items, int32_t *n_items);
+/* Download (for callers that built the set from an extractor). */
+int orbgpu_features_download(orbgpu_features *f, orbgpu_keypoint *keys_un, float *u_right, uint8_t *descriptors);
+
+enum {  /* orbgpu_search_policy.source */
+  ORBGPU_SRC_WINDOW = 0,      /* GetFeaturesInArea(u, v, r, min_level, max_level) */
+  ORBGPU_SRC_LIST = 1         /* cand[list_begin .. list_end) in list order (one vocabulary node) */
+};
+enum {  /* orbgpu_search_policy.ratio_mode */
+  ORBGPU_RATIO_NONE = 0,
+  ORBGPU_RATIO_SAME_LEVEL = 1, /* reject if level1 == level2 && d1 > ratio * d2            (ORBmatcher.cc:118-120) */
+  ORBGPU_RATIO_LESS = 2        /* accept only if (float)d1 < ratio * (float)d2             (ORBmatcher.cc:225, 454, 565) */
+};
+enum {  /* orbgpu_search_policy.greedy */
+  ORBGPU_GREEDY_NONE = 0,      /* queries are independent */
+  ORBGPU_GREEDY_TAKEN = 1,     /* an accepted match of a query with ORBGPU_Q_BLOCKS set makes its keypoint unavailable to
+                                  every later query (F.mvpMapPoints[idx] / vpMatched[idx] / vbMatched2[idx] tests) */
+  ORBGPU_GREEDY_DISTANCE = 2   /* SearchForInitialization: a keypoint matched earlier at distance d is unavailable to a later
+                                  query whose distance to it is >= d (vMatchedDistance, ORBmatcher.cc:447) */
+};
+enum {  /* orbgpu_search_policy.gate */
+  ORBGPU_GATE_NONE = 0,
+  ORBGPU_GATE_FUSE = 1,        /* chi-square reprojection gates of Fuse (ORBmatcher.cc:853-876): needs inv_level_sigma2 */
+  ORBGPU_GATE_EPIPOLAR = 2     /* SearchForTriangulation (ORBmatcher.cc:664-699): '<=' update (last minimum wins), stereo flags, epipole distance,
+                                  CheckDistEpipolarLine (:137-159): needs f12, ex, ey, level_sigma2, scale_factors */
+};
+#define ORBGPU_Q_BLOCKS 1      /* orbgpu_query.flags: this query's accepted match blocks later queries */
+#define ORBGPU_Q_STEREO 2      /* EPIPOLAR gate: the query keypoint has a right coordinate (bStereo1) */
+
+typedef struct orbgpu_query {
+  float u, v, r;                    /* window centre / half-size; EPIPOLAR gate: (u, v) = kp1.pt */
+  int32_t min_level, max_level;     /* octave < min_level skipped; max_level >= 0 && octave > max_level skipped */
+  float ur, ur_tol;                 /* stereo gate (policy.stereo_gate) and FUSE gate: projected right coordinate; tolerance */
+  int32_t list_begin, list_end;     /* ORBGPU_SRC_LIST */
+  int32_t flags;
+} orbgpu_query;                     /* 40 bytes */
+
+typedef struct orbgpu_search_policy {
+  int32_t source, ratio_mode, greedy, gate;
+  int32_t accept_max;               /* accept when d1 <= accept_max (TH_HIGH, TH_LOW, TH_LOW - 1 for '<', ORBdist) */
+  float ratio;                      /* ORBmatcher::mfNNratio */
+  int32_t stereo_gate;              /* 1: candidates with u_right > 0 need |q.ur - u_right| <= q.ur_tol (ORBmatcher.cc:94-98, 1307-1312) */
+  int32_t only_stereo;              /* EPIPOLAR gate: bOnlyStereo */
+  float ex, ey;                     /* EPIPOLAR gate: epipole in the candidate image */
+  float f12[9];                     /* EPIPOLAR gate: fundamental matrix, row-major */
+  float level_sigma2[16], inv_level_sigma2[16], scale_factors[16];
+} orbgpu_search_policy;
+
+typedef struct orbgpu_match {
+  int32_t idx;                      /* best candidate keypoint, -1 if none */
+  int32_t dist, dist2;              /* best / second-best distance (256 = none) */
+  int8_t level, level2;             /* their octaves (-1 = none) */
+  int8_t accepted;                  /* threshold + ratio test passed */
+  int8_t pad;
+} orbgpu_match;                     /* 16 bytes */
+
+/* Runs the candidate loops of one ORBmatcher routine: queries [nq] (host), their descriptors
+ * [nq][32] (host), `occupied` [features.n] bytes or NULL (keypoints unavailable from the start),
+ * `cand` [ncand] for ORBGPU_SRC_LIST.  Query order is the reference's loop order; the result is
+ * exactly what the sequential loops produce (greedy modes are resolved on the device by iterating
+ * the parallel search to its unique fixed point).  *iterations (optional) receives the passes used. */
+int orbgpu_search(orbgpu_features *f, const orbgpu_query *queries, const uint8_t *query_descriptors, int nq,
+                  const uint8_t *occupied, const int32_t *cand, int ncand, const orbgpu_search_policy *policy,
+                  orbgpu_match *result, int *iterations);
+/* Batched GetFeaturesInArea: result as CSR (offsets [nq+1], items up to `cap`); returns
+ * ORBGPU_E_CAPACITY (with offsets filled) if `cap` is too small. */
+int orbgpu_features_in_area(orbgpu_features *f, const orbgpu_query *queries, int nq, int32_t *offsets,
+                            int32_t *items, int cap);
 
 /* Measured integer-pipe peak (register-resident POPC loop): returns POPC lane-ops per second. */
 int orbgpu_measure_popc_peak(int device, double *popc_per_second, double *lop3_per_second);

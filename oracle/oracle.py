@@ -23,8 +23,8 @@ _f32p = C.POINTER(C.c_float)
 
 def build(force=False):
     so = os.path.join(_HERE, "liborb_oracle.so")
-    src = os.path.join(_HERE, "oracle_cpu.cpp")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "oracle_cpu.cpp"), os.path.join(_HERE, "oracle_search.cpp")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(x) for x in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "liborb_oracle.so"])
     return so
 
@@ -69,6 +69,12 @@ def lib():
         L.orb_oracle_stereo_batch.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                               C.c_int, C.c_int, C.c_int, C.c_long, C.c_float, C.c_float, C.c_int,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orb_oracle_features_create.restype = C.c_void_p
+        L.orb_oracle_features_create.argtypes = [C.c_void_p]
+        L.orb_oracle_features_destroy.argtypes = [C.c_void_p]
+        L.orb_oracle_features_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orb_oracle_features_in_area.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.orb_oracle_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -239,3 +245,53 @@ def sincos(angle):
     c, s = C.c_float(), C.c_float()
     lib().orb_oracle_sincos(float(angle), C.byref(c), C.byref(s))
     return c.value, s.value
+
+
+class OracleFeatures:
+    """CPU restatement (oracle_search.cpp) of a frame's grid and of the ORBmatcher candidate loops; same record
+    layouts as include/orbgpu.h (the ctypes structures are shared with the product's binding)."""
+
+    def __init__(self, keys_un, descriptors, u_right, geometry):
+        from refactored_orb_slam2_b200._lib import KP_DTYPE, FeaturesDesc
+        k = np.ascontiguousarray(keys_un, KP_DTYPE)
+        d = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+        u = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        desc = FeaturesDesc()
+        C.memmove(C.byref(desc), C.byref(geometry), C.sizeof(FeaturesDesc))
+        desc.n, desc.keys_un, desc.descriptors = len(k), _p(k), _p(d)
+        desc.u_right = _p(u) if u is not None else None
+        self.n = len(k)
+        self.ncells = desc.grid_cols * desc.grid_rows
+        self._h = C.c_void_p(lib().orb_oracle_features_create(C.byref(desc)))
+
+    def __del__(self):
+        try:
+            lib().orb_oracle_features_destroy(self._h)
+        except Exception:
+            pass
+
+    def grid(self):
+        start = np.empty(self.ncells + 1, np.int32)
+        items = np.empty(max(self.n, 1), np.int32)
+        n = C.c_int32()
+        lib().orb_oracle_features_grid(self._h, _p(start), _p(items), C.byref(n))
+        return start, items[:n.value].copy()
+
+    def in_area(self, queries):
+        q = np.ascontiguousarray(queries)
+        offsets = np.empty(len(q) + 1, np.int32)
+        items = np.empty(max(1, len(q) * max(self.n, 1)), np.int32) if len(q) * self.n < (1 << 24) else np.empty(1 << 24, np.int32)
+        lib().orb_oracle_features_in_area(self._h, _p(q), len(q), _p(offsets), _p(items), len(items))
+        return offsets, items[:offsets[-1]].copy()
+
+    def search(self, queries, query_descriptors, policy, occupied=None, cand=None):
+        from refactored_orb_slam2_b200._lib import MATCH_DTYPE
+        q = np.ascontiguousarray(queries)
+        d = np.ascontiguousarray(query_descriptors, np.uint8).reshape(-1, 32)
+        occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+        cd = np.zeros(1, np.int32) if cand is None else np.ascontiguousarray(cand, np.int32)
+        out = np.zeros(len(q), MATCH_DTYPE)
+        rc = lib().orb_oracle_search(self._h, _p(q), _p(d), len(q), _p(occ) if occ is not None else None, _p(cd), 0 if cand is None else len(cd),
+                                     C.byref(policy), _p(out))
+        assert rc == 0, rc
+        return out

@@ -13,6 +13,8 @@
 #include <cassert>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <list>
 #include <memory>
@@ -22,6 +24,7 @@ typedef unsigned char uchar;
 #define CV_PI 3.1415926535897932384626433832795
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5
 
 extern "C" {
 void orb_oracle_resize(const uint8_t *src, int sw, int sh, int sstep, uint8_t *dst, int dw, int dh, int dstep);
@@ -66,8 +69,11 @@ struct KeyPoint {
 // Mat::zeros returns an expression; assigning it to an existing Mat of the same size fills that Mat IN PLACE
 // (cv::MatExpr semantics: create() is a no-op for a matching buffer).  computeDescriptors relies on this to write
 // into a row range of the output matrix (ORBextractor.cc:969-971).
-struct ZerosExpr { int rows, cols; };
+struct ZerosExpr { int rows, cols, type; };
 
+// Element types: only CV_8U (ORBextractor.cc, image patches) and CV_32F (poses, points, patches in Frame.cc /
+// KeyFrame.cc / MapPoint.cc / ORBmatcher.cc) occur on the path.  Arithmetic is eager (no MatExpr fusion): products
+// accumulate in double and round once to float, like cv::gemm's float kernels; dot / norm return double.
 class Mat {
  public:
   struct Step { size_t v; operator size_t() const { return v; } };
@@ -75,38 +81,131 @@ class Mat {
   Step step{0};
   uchar *data = nullptr;
   Mat() {}
-  Mat(Size sz, int) { create(sz.height, sz.width, 0); }
-  Mat(int r, int c, int) { create(r, c, 0); }
-  Mat(int r, int c, int, void *ext, size_t s) : rows(r), cols(c), step{s}, data((uchar *)ext) {}
-  void create(int r, int c, int) {
-    if (data && r == rows && c == cols) return;     // cv::Mat::create keeps a matching buffer (ROI included)
-    rows = r; cols = c; step.v = (size_t)c;
-    own_ = std::shared_ptr<uchar>(new uchar[(size_t)r * c + 64], std::default_delete<uchar[]>());
+  Mat(Size sz, int t) { create(sz.height, sz.width, t); }
+  Mat(int r, int c, int t) { create(r, c, t); }
+  Mat(int r, int c, int t, void *ext, size_t s) : rows(r), cols(c), step{s}, data((uchar *)ext), type_(t) {}
+  static int esz(int t) { return t == CV_32F ? 4 : 1; }
+  void create(int r, int c, int t) {
+    if (data && r == rows && c == cols && t == type_) return;     // cv::Mat::create keeps a matching buffer (ROI included)
+    rows = r; cols = c; type_ = t; step.v = (size_t)c * esz(t);
+    own_ = std::shared_ptr<uchar>(new uchar[(size_t)r * step.v + 64], std::default_delete<uchar[]>());
     data = own_.get();
   }
   void release() { own_.reset(); data = nullptr; rows = cols = 0; step.v = 0; }
   bool empty() const { return !data || !rows || !cols; }
-  int type() const { return CV_8UC1; }
-  size_t step1() const { return step.v; }
+  int type() const { return type_; }
+  size_t step1() const { return step.v / esz(type_); }
+  bool isContinuous() const { return rows <= 1 || step.v == (size_t)cols * esz(type_); }
   template <class T> T &at(int r, int c) { return *(T *)(data + (size_t)r * step.v + c * sizeof(T)); }
   template <class T> const T &at(int r, int c) const { return *(const T *)(data + (size_t)r * step.v + c * sizeof(T)); }
+  // single-index access as cv::Mat::at(int i0): linear for continuous / row vectors, strided for column vectors
+  template <class T> T &at(int i) { return const_cast<T &>(static_cast<const Mat *>(this)->at<T>(i)); }
+  template <class T> const T &at(int i) const {
+    if (isContinuous() || rows == 1) return ((const T *)data)[i];
+    if (cols == 1) return *(const T *)(data + (size_t)i * step.v);
+    return *(const T *)(data + (size_t)(i / cols) * step.v + (i % cols) * sizeof(T));
+  }
   uchar *ptr(int r = 0) { return data + (size_t)r * step.v; }
   const uchar *ptr(int r = 0) const { return data + (size_t)r * step.v; }
-  Mat roi(int x, int y, int w, int h) const { Mat m; m.rows = h; m.cols = w; m.step = step; m.data = data + (size_t)y * step.v + x; m.own_ = own_; return m; }
+  template <class T> T *ptr(int r = 0) { return (T *)(data + (size_t)r * step.v); }
+  template <class T> const T *ptr(int r = 0) const { return (const T *)(data + (size_t)r * step.v); }
+  Mat roi(int x, int y, int w, int h) const {
+    Mat m; m.rows = h; m.cols = w; m.step = step; m.type_ = type_; m.data = data + (size_t)y * step.v + (size_t)x * esz(type_); m.own_ = own_;
+    return m;
+  }
   Mat operator()(const Rect &r) const { return roi(r.x, r.y, r.width, r.height); }
   Mat rowRange(int a, int b) const { return roi(0, a, cols, b - a); }
   Mat colRange(int a, int b) const { return roi(a, 0, b - a, rows); }
-  Mat clone() const { Mat m(rows, cols, 0); for (int r = 0; r < rows; r++) std::memcpy(m.ptr(r), ptr(r), cols); return m; }
-  static ZerosExpr zeros(int r, int c, int) { return ZerosExpr{r, c}; }
+  Mat row(int r) const { return roi(0, r, cols, 1); }
+  Mat col(int c) const { return roi(c, 0, 1, rows); }
+  Mat clone() const {
+    Mat m;
+    if (empty()) return m;
+    m.create(rows, cols, type_);
+    for (int r = 0; r < rows; r++) std::memcpy(m.ptr(r), ptr(r), (size_t)cols * esz(type_));
+    return m;
+  }
+  void copyTo(Mat &dst) const { dst.create(rows, cols, type_); for (int r = 0; r < rows; r++) std::memmove(dst.ptr(r), ptr(r), (size_t)cols * esz(type_)); }
+  void copyTo(Mat &&dst) const { copyTo(dst); }     // into an ROI header of matching size: written in place
+  Mat reshape(int) const { return *this; }           // only on the cv::undistortPoints path, which this stand-in does not provide
+  void convertTo(Mat &dst, int t) const {
+    Mat out(rows, cols, t);
+    for (int r = 0; r < rows; r++)
+      for (int c = 0; c < cols; c++) {
+        const float v = type_ == CV_32F ? at<float>(r, c) : (float)at<uchar>(r, c);
+        if (t == CV_32F) out.at<float>(r, c) = v; else out.at<uchar>(r, c) = (uchar)std::min(255.f, std::max(0.f, std::nearbyintf(v)));
+      }
+    dst = out;
+  }
+  Mat t() const { Mat m(cols, rows, type_); for (int r = 0; r < rows; r++) for (int c = 0; c < cols; c++) m.at<float>(c, r) = at<float>(r, c); return m; }
+  double dot(const Mat &o) const {
+    double s = 0;
+    for (int r = 0; r < rows; r++) for (int c = 0; c < cols; c++) s += (double)at<float>(r, c) * (double)o.at<float>(r, c);
+    return s;
+  }
+  static ZerosExpr zeros(int r, int c, int t) { return ZerosExpr{r, c, t}; }
+  static Mat ones(int r, int c, int t) { Mat m(r, c, t); for (int i = 0; i < r; i++) for (int j = 0; j < c; j++) m.at<float>(i, j) = 1.f; return m; }
+  static Mat eye(int r, int c, int t) { Mat m = ZerosExpr{r, c, t}; for (int i = 0; i < std::min(r, c); i++) m.at<float>(i, i) = 1.f; return m; }
   Mat(const ZerosExpr &e) { *this = e; }
   Mat &operator=(const ZerosExpr &e) {
-    create(e.rows, e.cols, 0);
-    for (int r = 0; r < rows; r++) std::memset(ptr(r), 0, cols);
+    create(e.rows, e.cols, e.type);
+    for (int r = 0; r < rows; r++) std::memset(ptr(r), 0, (size_t)cols * esz(type_));
     return *this;
   }
  private:
   std::shared_ptr<uchar> own_;
+  int type_ = CV_8U;
 };
+
+template <class T> class Mat_ : public Mat {         // only the comma initialiser (cv::Mat_<float>(3,1) << x, y, z) is used
+ public:
+  Mat_(int r, int c) : Mat(r, c, CV_32F) {}
+};
+template <class T> struct MatCommaInit {
+  Mat m; int i;
+  MatCommaInit &operator,(double v) { m.at<T>(i / m.cols, i % m.cols) = (T)v; i++; return *this; }
+  operator Mat() const { return m; }
+};
+template <class T> inline MatCommaInit<T> operator<<(const Mat_<T> &m, double v) { MatCommaInit<T> ci{m, 0}; return (ci, v); }
+
+inline Mat matBinary(const Mat &a, const Mat &b, int op) {
+  Mat m(a.rows, a.cols, CV_32F);
+  for (int r = 0; r < a.rows; r++)
+    for (int c = 0; c < a.cols; c++) m.at<float>(r, c) = op ? a.at<float>(r, c) - b.at<float>(r, c) : a.at<float>(r, c) + b.at<float>(r, c);
+  return m;
+}
+inline Mat operator+(const Mat &a, const Mat &b) { return matBinary(a, b, 0); }
+inline Mat operator-(const Mat &a, const Mat &b) { return matBinary(a, b, 1); }
+inline Mat matScale(const Mat &a, double s) {
+  Mat m(a.rows, a.cols, CV_32F);
+  for (int r = 0; r < a.rows; r++) for (int c = 0; c < a.cols; c++) m.at<float>(r, c) = (float)((double)a.at<float>(r, c) * s);
+  return m;
+}
+inline Mat operator-(const Mat &a) { return matScale(a, -1.0); }
+inline Mat operator*(const Mat &a, double s) { return matScale(a, s); }
+inline Mat operator*(double s, const Mat &a) { return matScale(a, s); }
+inline Mat operator/(const Mat &a, double s) { return matScale(a, 1.0 / s); }
+inline Mat operator*(const Mat &a, const Mat &b) {
+  Mat m(a.rows, b.cols, CV_32F);
+  for (int r = 0; r < a.rows; r++)
+    for (int c = 0; c < b.cols; c++) {
+      double s = 0;
+      for (int k = 0; k < a.cols; k++) s += (double)a.at<float>(r, k) * (double)b.at<float>(k, c);
+      m.at<float>(r, c) = (float)s;
+    }
+  return m;
+}
+enum { NORM_L1 = 2, NORM_L2 = 4 };
+inline double norm(const Mat &a) { return std::sqrt(a.dot(a)); }
+inline double norm(const Mat &a, const Mat &b, int /*NORM_L1*/) {
+  double s = 0;
+  for (int r = 0; r < a.rows; r++) for (int c = 0; c < a.cols; c++) s += std::fabs((double)a.at<float>(r, c) - (double)b.at<float>(r, c));
+  return s;
+}
+inline void undistortPoints(const Mat &, Mat &, const Mat &, const Mat &, const Mat &, const Mat &) {
+  fprintf(stderr, "cvshim: cv::undistortPoints is not provided (use zero distortion coefficients)\n");
+  abort();
+}
 
 class _InputArray {
  public:

@@ -3,9 +3,10 @@ sm_100a CUDA kernels behind a C ABI (include/orbgpu.h) and a host-side mirror of
 ORBextractor / ORBmatcher / Frame::ComputeStereoMatches interfaces.  No CPU fallback."""
 from ._lib import KP_DTYPE, TOP2_DTYPE, OrbGpuError, lib  # noqa: F401
 from .extractor import ORBextractor  # noqa: F401
+from .features import FrameFeatures, grid_geometry, make_policy  # noqa: F401
 from .matcher import DescriptorBank, ORBmatcher, merge_top2_device  # noqa: F401
 from .stereo import ComputeStereoMatches, Frame  # noqa: F401
 from .pipeline import StereoBatchPipeline  # noqa: F401
 
-__all__ = ["ORBextractor", "ORBmatcher", "DescriptorBank", "ComputeStereoMatches", "Frame", "StereoBatchPipeline", "merge_top2_device",
+__all__ = ["ORBextractor", "FrameFeatures", "grid_geometry", "make_policy", "ORBmatcher", "DescriptorBank", "ComputeStereoMatches", "Frame", "StereoBatchPipeline", "merge_top2_device",
            "KP_DTYPE", "TOP2_DTYPE", "OrbGpuError", "lib"]

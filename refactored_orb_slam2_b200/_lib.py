@@ -26,6 +26,27 @@ class ExtractorParams(C.Structure):
                 ("max_height", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32)]
 
 
+class FeaturesDesc(C.Structure):
+    _fields_ = [("n", C.c_int32), ("keys_un", C.c_void_p), ("u_right", C.c_void_p), ("descriptors", C.c_void_p),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("grid_w_inv", C.c_float), ("grid_h_inv", C.c_float),
+                ("grid_cols", C.c_int32), ("grid_rows", C.c_int32), ("query_min_x", C.c_float), ("query_min_y", C.c_float),
+                ("device", C.c_int32)]
+
+
+class SearchPolicy(C.Structure):
+    _fields_ = [("source", C.c_int32), ("ratio_mode", C.c_int32), ("greedy", C.c_int32), ("gate", C.c_int32),
+                ("accept_max", C.c_int32), ("ratio", C.c_float), ("stereo_gate", C.c_int32), ("only_stereo", C.c_int32),
+                ("ex", C.c_float), ("ey", C.c_float), ("f12", C.c_float * 9), ("level_sigma2", C.c_float * 16),
+                ("inv_level_sigma2", C.c_float * 16), ("scale_factors", C.c_float * 16)]
+
+
+QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("r", "<f4"), ("min_level", "<i4"), ("max_level", "<i4"), ("ur", "<f4"),
+                        ("ur_tol", "<f4"), ("list_begin", "<i4"), ("list_end", "<i4"), ("flags", "<i4")])     # orbgpu_query, 40 bytes
+MATCH_DTYPE = np.dtype([("idx", "<i4"), ("dist", "<i4"), ("dist2", "<i4"), ("level", "i1"), ("level2", "i1"), ("accepted", "i1"),
+                        ("pad", "i1")])                                                                        # orbgpu_match, 16 bytes
+assert QUERY_DTYPE.itemsize == 40 and MATCH_DTYPE.itemsize == 16
+
+
 class OrbGpuError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("orbgpu error %d: %s" % (code, msg))
@@ -64,6 +85,14 @@ SYMBOLS = {
     "orbgpu_hamming_top2_dense_device": (_i, [_vp, _vp, _i, _vp, _vp]),
     "orbgpu_top2_merge_device": (_i, [_vp, _i, _i, _vp, _f, _i, _vp, _i, _vp]),
     "orbgpu_hamming_top2_csr": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i]),
+    "orbgpu_features_create": (_i, [C.POINTER(FeaturesDesc), C.POINTER(_vp)]),
+    "orbgpu_features_from_extractor": (_i, [_vp, _i, _i, C.POINTER(FeaturesDesc), C.POINTER(_vp)]),
+    "orbgpu_features_destroy": (None, [_vp]),
+    "orbgpu_features_count": (_i, [_vp]),
+    "orbgpu_features_grid": (_i, [_vp, _vp, _vp, C.POINTER(C.c_int32)]),
+    "orbgpu_features_download": (_i, [_vp, _vp, _vp, _vp]),
+    "orbgpu_search": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, C.POINTER(SearchPolicy), _vp, C.POINTER(_i)]),
+    "orbgpu_features_in_area": (_i, [_vp, _vp, _i, _vp, _vp, _i]),
     "orbgpu_measure_popc_peak": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "orbgpu_measure_pipe": (_i, [_i, _i, C.POINTER(C.c_double)]),
     "orbgpu_launch_count": (_i64, [_i]),

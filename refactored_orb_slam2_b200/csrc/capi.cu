@@ -801,6 +801,27 @@ int orbgpu_stereo_match(orbgpu_extractor *L, orbgpu_extractor *R, int first_left
   return check_status(L);
 }
 
+// Used by search.cu (orbgpu_features_from_extractor): device pointers of image `image` of the last batch and, when
+// pair >= 0, row `pair` of the stereo results of the last orbgpu_stereo_match on this (left) handle.
+extern "C" int orbgpu_internal_extractor_view(orbgpu_extractor *e, int image, int pair, const orbgpu_keypoint **kps, const uint8_t **desc,
+                                              int *count, const float **uRight, int *device, void **stream) {
+  if (image < 0 || image >= e->lastBatch) { set_error("image %d outside the last batch (%d)", image, e->lastBatch); return ORBGPU_E_INVALID; }
+  if (pair >= 0 && (!e->dURight || pair >= e->p.max_batch)) { set_error("no stereo result row %d on this handle", pair); return ORBGPU_E_INVALID; }
+  DeviceGuard guard(e->device);
+  int n = 0;
+  ORBGPU_CUDA_CHECK(cudaMemcpyAsync(&n, e->dKpCount + image, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  ORBGPU_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  int rc = check_status(e);
+  if (rc) return rc;
+  *kps = e->dKps + (size_t)image * e->kpCap;
+  *desc = e->dDesc + (size_t)image * e->kpCap * 32;
+  *count = std::min(n, e->kpCap);
+  *uRight = pair >= 0 ? e->dURight + (size_t)pair * e->kpCap : nullptr;
+  *device = e->device;
+  *stream = (void *)e->stream;
+  return ORBGPU_OK;
+}
+
 // ---------------------------------------------------------------- matcher
 
 int orbgpu_bank_wrap_device(const uint8_t *d_descriptors, int rows, int64_t index_base, int device, orbgpu_bank **out) {

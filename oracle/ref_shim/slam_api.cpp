@@ -6,16 +6,19 @@
 //
 //   oracle/_ref/libref_slam.so        + the reference's own src/ORBmatcher.cc                  -> the checker
 //   oracle/_ref/libshim_slam_cpu.so   + shim/ORBmatcher.cc on the CPU oracle backend           -> pins host policy + oracle
-//   oracle/_ref/libshim_slam_gpu.so   + shim/ORBmatcher.cc on liborbgpu.so (the product path)  -> GPU parity tests
+//   oracle/_ref/libshim_slam_gpu.so   + shim/ORBmatcher.cc AND shim/ORBextractor.cc (instead of the reference's) on
+//                                       liborbgpu.so: the reference linked against the drop-in -> GPU parity tests
 //
 // A "scene" is a small map built from flat arrays (frames with keypoints / descriptors / right coordinates, keyframes
 // made from them, MapPoints with observations).  Every run_* function calls one public ORBmatcher method exactly as
 // Tracking / LocalMapping / LoopClosing do (call sites in SURVEY.md section 3.3) and the dump functions flatten the
 // state it left behind, so two builds can be compared output by output from Python (tests/test_matcher_ref.py).
 #include <cmath>
+#include <cstddef>
 #include <cstdint>
 #include <cstring>
 #include <map>
+#include <new>
 #include <set>
 #include <thread>
 #include <vector>
@@ -28,6 +31,9 @@
 #include "MapPoint.h"
 #include "ORBextractor.h"
 #include "ORBmatcher.h"
+#ifdef SLAM_SHIM_EXTRACTOR
+#include "FrameStereo.h"
+#endif
 #undef private
 #undef protected
 
@@ -300,6 +306,7 @@ int slam_descriptor_distance(const uint8_t *a, const uint8_t *b) {
   return ORBmatcher::DescriptorDistance(A, B);
 }
 
+#ifndef SLAM_SHIM_EXTRACTOR
 // ---- Frame::ComputeStereoMatches (Frame.cc:477-646), the reference's own code ----------------------------------------------
 // Keypoints and descriptors are given (the octree's tie-break makes the reference's own extraction allocator-dependent,
 // see ref_api.cpp); the pyramids are built by the reference's ORBextractor::ComputePyramid from the two images.
@@ -324,6 +331,50 @@ int slam_compute_stereo(int nfeatures, float scaleFactor, int nlevels, int iniTh
   int matched = 0;
   for (int i = 0; i < nL; i++) { uRight[i] = F.mvuRight[i]; depth[i] = F.mvDepth[i]; matched += F.mvuRight[i] >= 0; }
   return matched;
+}
+
+#endif
+
+// ---- the reference's own stereo Frame constructor (Frame.cc:66-127) -------------------------------------------------------
+// Two extractor threads, UndistortKeyPoints, ComputeStereoMatches, image bounds, AssignFeaturesToGrid — all the
+// reference's code; which ORBextractor / ORBmatcher it runs on depends on the build (reference's own, or the drop-in
+// shims on liborbgpu.so).  The constructor reads `mb` before assigning it (Frame.cc:505 vs :124), so the object is
+// constructed in storage where that member already holds the intended mbf / fx.
+int slam_stereo_frame(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, const uint8_t *left, const uint8_t *right, int w,
+                      int hgt, float fx, float fy, float cx, float cy, float bf, float thDepth, int cap, RefKp *keys, uint8_t *desc,
+                      float *uRight, float *depth, int *cellStart, int *items, float *uRightDevice, float *depthDevice) {
+  ORBextractor exL(nfeatures, scaleFactor, nlevels, iniTh, minTh), exR(nfeatures, scaleFactor, nlevels, iniTh, minTh);
+  const float k[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
+  cv::Mat K = mat_from(k, 3, 3), dist = cv::Mat::zeros(4, 1, CV_32F);
+  cv::Mat imL(hgt, w, CV_8UC1, (void *)left, (size_t)w), imR(hgt, w, CV_8UC1, (void *)right, (size_t)w);
+  Frame::mbInitialComputations = true;
+  std::vector<char> storage(sizeof(Frame) + 64, 0);
+  char *raw = storage.data() + (64 - (uintptr_t)storage.data() % 64) % 64;
+  *(float *)(raw + offsetof(Frame, mb)) = bf / fx;
+  Frame *F = new (raw) Frame(imL, imR, 0.0, &exL, &exR, nullptr, K, dist, bf, thDepth);
+  const int n = F->N;
+  if (n <= cap) {
+    for (int i = 0; i < n; i++) {
+      std::memcpy(&keys[i], &F->mvKeysUn[i], sizeof(RefKp));
+      std::memcpy(desc + (size_t)i * 32, F->mDescriptors.ptr(i), 32);
+      uRight[i] = F->mvuRight[i]; depth[i] = F->mvDepth[i];
+    }
+    int c = 0;
+    for (int ix = 0; ix < FRAME_GRID_COLS; ix++)
+      for (int iy = 0; iy < FRAME_GRID_ROWS; iy++) {
+        cellStart[ix * FRAME_GRID_ROWS + iy] = c;
+        for (size_t v : F->mGrid[ix][iy]) items[c++] = (int)v;
+      }
+    cellStart[FRAME_GRID_COLS * FRAME_GRID_ROWS] = c;
+#ifdef SLAM_SHIM_EXTRACTOR
+    // the same frame through the device-side replacement of the method's body (shim/FrameStereo.h)
+    std::vector<float> u, z;
+    ComputeStereoMatchesGPU(exL, exR, bf, bf / fx, n, u, z);
+    for (int i = 0; i < n; i++) { uRightDevice[i] = u[i]; depthDevice[i] = z[i]; }
+#endif
+  }
+  F->~Frame();
+  return n;
 }
 
 }  // extern "C"

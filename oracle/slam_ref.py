@@ -70,6 +70,20 @@ class SlamLib:
         L.slam_descriptor_distance.argtypes = [_p, _p]
         L.slam_compute_stereo.argtypes = [_i, _f, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _p, _i, _f, _f, _p, _p]
 
+    def stereo_frame(self, params, left, right, fx, fy, cx, cy, bf, th_depth=35.0, cap=20000):
+        """The reference's stereo Frame constructor (Frame.cc:66-127) on this build's ORBextractor / ORBmatcher."""
+        nf, sf, nl, ini, mn = params
+        left, right = np.ascontiguousarray(left), np.ascontiguousarray(right)
+        keys, desc = np.zeros(cap, KP), np.zeros((cap, 32), np.uint8)
+        u, z, u2, z2 = (np.full(cap, np.nan, np.float32) for _ in range(4))
+        start, items = np.zeros(64 * 48 + 1, np.int32), np.zeros(cap, np.int32)
+        self.L.slam_stereo_frame.argtypes = [_i, _f, _i, _i, _i, _p, _p, _i, _i, _f, _f, _f, _f, _f, _f, _i] + [_p] * 8
+        n = self.L.slam_stereo_frame(nf, sf, nl, ini, mn, _ptr(left), _ptr(right), left.shape[1], left.shape[0], fx, fy, cx, cy, bf, th_depth, cap,
+                                     _ptr(keys), _ptr(desc), _ptr(u), _ptr(z), _ptr(start), _ptr(items), _ptr(u2), _ptr(z2))
+        assert 0 <= n <= cap
+        return dict(keys=keys[:n], desc=desc[:n], u_right=u[:n], depth=z[:n], cell_start=start, cell_items=items[:start[-1]],
+                    u_right_device=u2[:n], depth_device=z2[:n])
+
     def compute_stereo(self, params, left, right, kL, dL, kR, dR, mbf, mb):
         nf, sf, nl, ini, mn = params
         left, right = np.ascontiguousarray(left), np.ascontiguousarray(right)

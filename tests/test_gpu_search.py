@@ -210,3 +210,28 @@ def test_shim_matcher_on_gpu_equals_reference_matcher(pkg, seed, small):
     mine = slam_scenarios.run_all("shim_gpu", seed, small)
     assert slam_scenarios.compare(ref, mine) == []
     assert len(ref) == 21
+
+
+@pytest.mark.skipif(not slam_ref.available("shim_gpu"), reason="oracle/_ref checker libraries not shipped with this snapshot")
+@pytest.mark.parametrize("w,h,nf,seed,cam", [(1241, 376, 2000, 2, (718.856, 607.1928, 185.2157, 386.1448)), (752, 480, 1200, 1000, (435.2047, 367.4517, 252.2008, 47.9064))])
+def test_reference_frame_constructor_linked_against_the_drop_in(pkg, w, h, nf, seed, cam):
+    """The reference's OWN Frame::Frame(stereo) (Frame.cc:66-127, unmodified) compiled against shim/ORBextractor + shim/ORBmatcher
+    on liborbgpu.so: keypoints, descriptors, mvuRight / mvDepth (the reference's host ComputeStereoMatches on the pyramid the shim
+    downloads) and the grid must equal the oracle's; so must the device replacement of the method body (shim/FrameStereo.h)."""
+    fx, cx, cy, bf = cam
+    left, right = gen_synth.stereo_pair(h, w, seed)
+    params = (nf, 1.2, 8, 20, 7)
+    out = slam_ref.SlamLib("shim_gpu").stereo_frame(params, left, right, fx, fx, cx, cy, bf)
+    ol, orr = oracle.OracleExtractor(*params), oracle.OracleExtractor(*params)
+    (kl, dl), (kr, dr) = ol(left), orr(right)
+    assert len(out["keys"]) == len(kl)
+    for f in kl.dtype.names:
+        assert np.array_equal(out["keys"][f], kl[f]), f
+    assert np.array_equal(out["desc"], dl)
+    mb = np.float32(np.float32(bf) / np.float32(fx))
+    ou, oz, _, _ = oracle.stereo(ol, orr, kl, dl, kr, dr, bf, mb)
+    assert np.array_equal(out["u_right"], ou) and np.array_equal(out["depth"], oz)
+    assert np.array_equal(out["u_right_device"], ou) and np.array_equal(out["depth_device"], oz)
+    geo = pkg.grid_geometry(0.0, float(w), 0.0, float(h))
+    start, items = oracle.OracleFeatures(kl, dl, ou, geo).grid()
+    assert np.array_equal(start, out["cell_start"]) and np.array_equal(items, out["cell_items"])

@@ -68,3 +68,16 @@ def test_descriptor_distance_is_the_reference_popcount():
     for i in range(len(a)):
         r = L.slam_descriptor_distance(slam_ref._ptr(a[i]), slam_ref._ptr(b[i]))
         assert r == want[i] == oracle.hamming(a[i], b[i]) == S.slam_descriptor_distance(slam_ref._ptr(a[i]), slam_ref._ptr(b[i]))
+
+
+def test_reference_stereo_frame_constructor_grid_equals_oracle_grid():
+    """Frame::Frame(stereo) of the reference, whole (two extractor threads, ComputeStereoMatches, ComputeImageBounds,
+    AssignFeaturesToGrid): the grid it builds for ITS keypoints equals the oracle's grid restatement."""
+    import refactored_orb_slam2_b200 as pkg
+    left, right = gen_synth.stereo_pair(240, 416, 11)
+    out = slam_ref.SlamLib("ref").stereo_frame((500, 1.2, 8, 20, 7), left, right, 718.856, 718.856, 208.0, 120.0, 386.1448)
+    assert len(out["keys"]) > 400 and (out["u_right"] >= 0).sum() > 50
+    geo = pkg.grid_geometry(0.0, 416.0, 0.0, 240.0)
+    o = oracle.OracleFeatures(out["keys"], out["desc"], out["u_right"], geo)
+    start, items = o.grid()
+    assert np.array_equal(start, out["cell_start"]) and np.array_equal(items, out["cell_items"])

@@ -68,7 +68,8 @@ class SlamLib:
         L.slam_fuse_sim3.argtypes = [_p, _i, _p, _p, _i, _f, _p, _f]
         L.slam_search_by_sim3.argtypes = [_p, _i, _i, _p, _f, _p, _p, _f, _f]
         L.slam_descriptor_distance.argtypes = [_p, _p]
-        L.slam_compute_stereo.argtypes = [_i, _f, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _p, _i, _f, _f, _p, _p]
+        if hasattr(L, "slam_compute_stereo"):       # absent from the build whose ORBextractor is the drop-in (no ComputePyramid member)
+            L.slam_compute_stereo.argtypes = [_i, _f, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _p, _i, _f, _f, _p, _p]
 
     def stereo_frame(self, params, left, right, fx, fy, cx, cy, bf, th_depth=35.0, cap=20000):
         """The reference's stereo Frame constructor (Frame.cc:66-127) on this build's ORBextractor / ORBmatcher."""

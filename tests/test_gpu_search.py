@@ -235,3 +235,32 @@ def test_reference_frame_constructor_linked_against_the_drop_in(pkg, w, h, nf, s
     geo = pkg.grid_geometry(0.0, float(w), 0.0, float(h))
     start, items = oracle.OracleFeatures(kl, dl, ou, geo).grid()
     assert np.array_equal(start, out["cell_start"]) and np.array_equal(items, out["cell_items"])
+
+
+def test_concurrent_searches_from_three_threads_share_one_feature_set(pkg):
+    """Tracking, LocalMapping and LoopClosing search concurrently in the reference (SURVEY 8b threading): per-thread stream and
+    scratch inside orbgpu_search, read-only feature sets."""
+    import threading
+    W, V = make_view(13)
+    g, o = both(pkg, V)
+    jobs = []
+    for t in range(3):
+        rng = np.random.default_rng(100 + t)
+        q, d, _ = random_window_queries(pkg, rng, V, 1500 + 400 * t)
+        P = pkg.make_policy(greedy=1 if t != 1 else 2, ratio_mode=2 if t == 1 else 0, ratio=0.9, accept_max=100, stereo_gate=int(t == 0))
+        jobs.append((q, d, P, o.search(q, d, P)))
+    bad = []
+
+    def work(job):
+        q, d, P, want = job
+        for _ in range(25):
+            got, _ = g.search(q, d, P)
+            if not np.array_equal(got, want):
+                bad.append(1)
+
+    th = [threading.Thread(target=work, args=(j,)) for j in jobs]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not bad

@@ -18,6 +18,8 @@
 #include <cstring>
 #include <list>
 #include <memory>
+#include <sstream>
+#include <string>
 #include <vector>
 
 typedef unsigned char uchar;
@@ -84,6 +86,7 @@ class Mat {
   Mat(Size sz, int t) { create(sz.height, sz.width, t); }
   Mat(int r, int c, int t) { create(r, c, t); }
   Mat(int r, int c, int t, void *ext, size_t s) : rows(r), cols(c), step{s}, data((uchar *)ext), type_(t) {}
+  Mat(int r, int c, int t, void *ext) : rows(r), cols(c), step{(size_t)c * esz(t)}, data((uchar *)ext), type_(t) {}
   static int esz(int t) { return t == CV_32F ? 4 : 1; }
   void create(int r, int c, int t) {
     if (data && r == rows && c == cols && t == type_) return;     // cv::Mat::create keeps a matching buffer (ROI included)
@@ -269,6 +272,37 @@ inline void FAST(const Mat &img, std::vector<KeyPoint> &kps, int threshold, bool
   kps.clear();
   for (int i = 0; i < n; i++) kps.push_back(KeyPoint((float)buf[3 * i], (float)buf[3 * i + 1], 7.f, -1.f, (float)buf[3 * i + 2]));
 }
+
+// cv::FileStorage / cv::FileNode: only so that DBoW2's YAML save / load members (virtual, hence instantiated) compile;
+// the checker loads vocabularies through the reference's own text / binary loaders (ORBVocabulary.cc) instead.
+struct FileNode;
+struct FileNodeIterator {
+  int i = 0;
+  FileNodeIterator &operator++() { i++; return *this; }
+  bool operator!=(const FileNodeIterator &o) const { return i != o.i; }
+  inline FileNode operator*() const;
+};
+struct FileNode {
+  FileNodeIterator begin() const { return FileNodeIterator(); }
+  FileNodeIterator end() const { return FileNodeIterator(); }
+  FileNode operator[](const std::string &) const { return FileNode(); }
+  FileNode operator[](const char *) const { return FileNode(); }
+  FileNode operator[](int) const { return FileNode(); }
+  size_t size() const { return 0; }
+  operator int() const { return 0; }
+  operator double() const { return 0; }
+  operator std::string() const { return std::string(); }
+};
+inline FileNode FileNodeIterator::operator*() const { return FileNode(); }
+struct FileStorage {
+  enum { READ = 0, WRITE = 1 };
+  FileStorage() {}
+  FileStorage(const std::string &, int) { fprintf(stderr, "cvshim: cv::FileStorage is not provided\n"); abort(); }
+  bool isOpened() const { return false; }
+  void release() {}
+  FileNode operator[](const std::string &) const { return FileNode(); }
+  template <class T> FileStorage &operator<<(const T &) { return *this; }
+};
 
 struct KeyPointsFilter {   // only reached from ComputeKeyPointsOld, which the reference never calls (ORBextractor.cc:992)
   static void retainBest(std::vector<KeyPoint> &k, int n) {

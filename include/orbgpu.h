@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORBGPU_VERSION 110
+#define ORBGPU_VERSION 120
 
 enum {
   ORBGPU_OK = 0,
@@ -285,6 +285,36 @@ int orbgpu_search(orbgpu_features *f, const orbgpu_query *queries, const uint8_t
  * ORBGPU_E_CAPACITY (with offsets filled) if `cap` is too small. */
 int orbgpu_features_in_area(orbgpu_features *f, const orbgpu_query *queries, int nq, int32_t *offsets,
                             int32_t *items, int cap);
+
+/* ------------------------------------------------------------------------------------------------
+ * DBoW2 vocabulary tree descent
+ *
+ * Frame::ComputeBoW / KeyFrame::ComputeBoW (src/Frame.cc:412-417, src/KeyFrame.cc:63-72) call
+ * TemplatedVocabulary::transform(features, BowVector, FeatureVector, levelsup = 4), whose cost is the
+ * per-feature descent of Source/ThirdParty/DBoW2/DBoW2-local/include/DBoW2/TemplatedVocabulary.h:1216-1258:
+ * at every level FORB::distance (…/src/FORB.cpp:77-100, a 256-bit popcount) to each of the k children,
+ * strict '<' (first child wins ties), until a leaf; the word is the leaf's word id and the
+ * FeatureVector node is the node passed at level L - levelsup.  The tree lives in HBM; the
+ * BowVector / FeatureVector std::maps and their normalisation stay host-side DBoW2 code
+ * (shim/ORBVocabularyGPU.h).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct orbgpu_vocabulary orbgpu_vocabulary;
+/* Flat tree as DBoW2 holds it: node 0 is the root, node i's children are
+ * children[child_start[i] .. child_start[i+1]) in m_nodes[i].children order, descriptors [nodes][32],
+ * word_id[i] = DBoW2 word id of a leaf (a node without children), ignored for inner nodes.
+ * depth_levels = m_L. */
+int orbgpu_vocabulary_create(int32_t nodes, const int32_t *child_start, const int32_t *children,
+                             const uint8_t *descriptors, const int32_t *word_id, int32_t depth_levels, int device,
+                             orbgpu_vocabulary **out);
+void orbgpu_vocabulary_destroy(orbgpu_vocabulary *v);
+/* n host descriptors [n][32] -> word_ids[n], node_ids[n].  node_ids[i] = 0 when depth_levels - levelsup <= 0
+ * (TemplatedVocabulary.h:1225); when the descent reaches a leaf ABOVE that level the reference leaves
+ * its output uninitialised — here the leaf's own node id is returned. */
+int orbgpu_vocabulary_transform(orbgpu_vocabulary *v, const uint8_t *descriptors, int n, int levelsup,
+                                int32_t *word_ids, int32_t *node_ids);
+/* The same for the descriptors of a device-resident feature set (no upload). */
+int orbgpu_vocabulary_transform_features(orbgpu_vocabulary *v, orbgpu_features *f, int levelsup, int32_t *word_ids,
+                                         int32_t *node_ids);
 
 /* Measured integer-pipe peak (register-resident POPC loop): returns POPC lane-ops per second. */
 int orbgpu_measure_popc_peak(int device, double *popc_per_second, double *lop3_per_second);

@@ -74,6 +74,7 @@ def lib():
         L.orb_oracle_features_destroy.argtypes = [C.c_void_p]
         L.orb_oracle_features_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orb_oracle_features_in_area.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.orb_oracle_voc_transform.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orb_oracle_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
@@ -295,3 +296,14 @@ class OracleFeatures:
                                      C.byref(policy), _p(out))
         assert rc == 0, rc
         return out
+
+
+def voc_transform(child_start, children, node_desc, word_id, depth_levels, features, levelsup):
+    """Restated DBoW2 tree descent (oracle_search.cpp): (word_ids, node_ids) per feature."""
+    cs, ch = np.ascontiguousarray(child_start, np.int32), np.ascontiguousarray(children, np.int32)
+    nd, wi = np.ascontiguousarray(node_desc, np.uint8), np.ascontiguousarray(word_id, np.int32)
+    f = np.ascontiguousarray(features, np.uint8).reshape(-1, 32)
+    words, nodes = np.zeros(len(f), np.int32), np.zeros(len(f), np.int32)
+    rc = lib().orb_oracle_voc_transform(len(wi), _p(cs), _p(ch), _p(nd), _p(wi), int(depth_levels), _p(f), len(f), int(levelsup), _p(words), _p(nodes))
+    assert rc == 0
+    return words, nodes

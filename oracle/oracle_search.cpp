@@ -225,3 +225,53 @@ int orb_oracle_search(const OracleFeatures *F, const orbgpu_query *queries, cons
 }
 
 }  // extern "C"
+
+// ---- DBoW2 vocabulary tree descent -----------------------------------------------------------------------------------
+// TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup)
+//   (Source/ThirdParty/DBoW2/DBoW2-local/include/DBoW2/TemplatedVocabulary.h:1216-1258) with FORB::distance
+//   (…/src/FORB.cpp:77-100: 64-bit SWAR popcount over 4 words, returned as double).
+// Where the reference leaves *nid uninitialised (leaf above level L - levelsup) the leaf's node id is reported.
+namespace {
+inline double forb_distance(const uint8_t *a, const uint8_t *b) {
+  uint64_t pa[4], pb[4];
+  std::memcpy(pa, a, 32);
+  std::memcpy(pb, b, 32);
+  uint64_t v, ret = 0;
+  for (size_t i = 0; i < 4; ++i) {
+    v = pa[i] ^ pb[i];
+    v = v - ((v >> 1) & (uint64_t) ~(uint64_t)0 / 3);
+    v = (v & (uint64_t) ~(uint64_t)0 / 15 * 3) + ((v >> 2) & (uint64_t) ~(uint64_t)0 / 15 * 3);
+    v = (v + (v >> 4)) & (uint64_t) ~(uint64_t)0 / 255 * 15;
+    ret += (uint64_t)(v * ((uint64_t) ~(uint64_t)0 / 255)) >> (sizeof(uint64_t) - 1) * 8;
+  }
+  return static_cast<double>(ret);
+}
+}  // namespace
+
+extern "C" int orb_oracle_voc_transform(int nodes, const int32_t *childStart, const int32_t *children, const uint8_t *nodeDesc, const int32_t *wordId,
+                                        int depthLevels, const uint8_t *features, int n, int levelsup, int32_t *wordIds, int32_t *nodeIds) {
+  (void)nodes;
+  const int nid_level = depthLevels - levelsup;
+  for (int f = 0; f < n; f++) {
+    const uint8_t *feature = features + (size_t)f * 32;
+    bool nidSet = false;
+    int nid = 0;
+    if (nid_level <= 0) { nid = 0; nidSet = true; }                 // :1225
+    int final_id = 0, current_level = 0;
+    while (childStart[final_id] != childStart[final_id + 1]) {      // do { ... } while (!isLeaf); an empty tree is handled by the caller (:1131)
+      ++current_level;
+      const int cs = childStart[final_id], ce = childStart[final_id + 1];
+      final_id = children[cs];
+      double best_d = forb_distance(feature, nodeDesc + (size_t)final_id * 32);
+      for (int c = cs + 1; c < ce; c++) {
+        const int id = children[c];
+        const double d = forb_distance(feature, nodeDesc + (size_t)id * 32);
+        if (d < best_d) { best_d = d; final_id = id; }
+      }
+      if (current_level == nid_level) { nid = final_id; nidSet = true; }
+    }
+    wordIds[f] = wordId[final_id];
+    nodeIds[f] = nidSet ? nid : final_id;
+  }
+  return ORBGPU_OK;
+}

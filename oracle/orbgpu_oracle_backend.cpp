@@ -1,12 +1,14 @@
 // orbgpu_oracle_backend.cpp — TEST INFRASTRUCTURE.  NOT part of the product and never linked into liborbgpu.so.
 //
-// Implements the four entry points of include/orbgpu.h that shim/ORBmatcher.cc calls (orbgpu_features_create / _destroy,
-// orbgpu_search, orbgpu_last_error) on top of the CPU oracle (oracle_search.cpp), so that the HOST policy of the shim —
+// Implements the entry points of include/orbgpu.h that shim/ORBmatcher.cc and shim/ORBVocabularyGPU.h call
+// (orbgpu_features_create / _destroy, orbgpu_search, orbgpu_vocabulary_create / _destroy / _transform, orbgpu_last_error)
+// on top of the CPU oracle (oracle_search.cpp), so that the HOST policy of the shim —
 // query construction before the candidate loops, pointer-graph updates after them — can be compared with the
 // reference's own ORBmatcher.cc (oracle/_ref/libref_slam.so) in the CPU test suite, and so that the oracle's
 // restatement of the candidate loops is itself pinned to the reference.  The GPU tests link the same shim against the
 // real liborbgpu.so instead.
 #include <cstdint>
+#include <vector>
 
 #include "../include/orbgpu.h"
 
@@ -16,6 +18,28 @@ OracleFeatures *orb_oracle_features_create(const orbgpu_features_desc *desc);
 void orb_oracle_features_destroy(OracleFeatures *F);
 int orb_oracle_search(const OracleFeatures *F, const orbgpu_query *queries, const uint8_t *qdesc, int nq, const uint8_t *occupied,
                       const int32_t *cand, int ncand, const orbgpu_search_policy *P, orbgpu_match *result);
+
+int orb_oracle_voc_transform(int nodes, const int32_t *childStart, const int32_t *children, const uint8_t *nodeDesc, const int32_t *wordId,
+                             int depthLevels, const uint8_t *features, int n, int levelsup, int32_t *wordIds, int32_t *nodeIds);
+
+struct OracleVoc { std::vector<int32_t> childStart, children, wordId; std::vector<uint8_t> desc; int depth; };
+int orbgpu_vocabulary_create(int32_t nodes, const int32_t *child_start, const int32_t *children, const uint8_t *descriptors, const int32_t *word_id,
+                             int32_t depth_levels, int, orbgpu_vocabulary **out) {
+  OracleVoc *v = new OracleVoc;
+  v->childStart.assign(child_start, child_start + nodes + 1);
+  v->children.assign(children, children + child_start[nodes]);
+  v->wordId.assign(word_id, word_id + nodes);
+  v->desc.assign(descriptors, descriptors + (size_t)nodes * 32);
+  v->depth = depth_levels;
+  *out = reinterpret_cast<orbgpu_vocabulary *>(v);
+  return ORBGPU_OK;
+}
+void orbgpu_vocabulary_destroy(orbgpu_vocabulary *v) { delete reinterpret_cast<OracleVoc *>(v); }
+int orbgpu_vocabulary_transform(orbgpu_vocabulary *h, const uint8_t *descriptors, int n, int levelsup, int32_t *word_ids, int32_t *node_ids) {
+  OracleVoc *v = reinterpret_cast<OracleVoc *>(h);
+  return orb_oracle_voc_transform((int)v->wordId.size(), v->childStart.data(), v->children.data(), v->desc.data(), v->wordId.data(), v->depth, descriptors, n,
+                                  levelsup, word_ids, node_ids);
+}
 
 int orbgpu_features_create(const orbgpu_features_desc *desc, orbgpu_features **out) {
   *out = reinterpret_cast<orbgpu_features *>(orb_oracle_features_create(desc));

@@ -7,6 +7,7 @@ from .features import FrameFeatures, grid_geometry, make_policy  # noqa: F401
 from .matcher import DescriptorBank, ORBmatcher, merge_top2_device  # noqa: F401
 from .stereo import ComputeStereoMatches, Frame  # noqa: F401
 from .pipeline import StereoBatchPipeline  # noqa: F401
+from .vocabulary import Vocabulary  # noqa: F401
 
-__all__ = ["ORBextractor", "FrameFeatures", "grid_geometry", "make_policy", "ORBmatcher", "DescriptorBank", "ComputeStereoMatches", "Frame", "StereoBatchPipeline", "merge_top2_device",
+__all__ = ["ORBextractor", "FrameFeatures", "grid_geometry", "make_policy", "Vocabulary", "ORBmatcher", "DescriptorBank", "ComputeStereoMatches", "Frame", "StereoBatchPipeline", "merge_top2_device",
            "KP_DTYPE", "TOP2_DTYPE", "OrbGpuError", "lib"]

@@ -93,6 +93,10 @@ SYMBOLS = {
     "orbgpu_features_download": (_i, [_vp, _vp, _vp, _vp]),
     "orbgpu_search": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, C.POINTER(SearchPolicy), _vp, C.POINTER(_i)]),
     "orbgpu_features_in_area": (_i, [_vp, _vp, _i, _vp, _vp, _i]),
+    "orbgpu_vocabulary_create": (_i, [C.c_int32, _vp, _vp, _vp, _vp, C.c_int32, _i, C.POINTER(_vp)]),
+    "orbgpu_vocabulary_destroy": (None, [_vp]),
+    "orbgpu_vocabulary_transform": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "orbgpu_vocabulary_transform_features": (_i, [_vp, _vp, _i, _vp, _vp]),
     "orbgpu_measure_popc_peak": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "orbgpu_measure_pipe": (_i, [_i, _i, C.POINTER(C.c_double)]),
     "orbgpu_launch_count": (_i64, [_i]),

@@ -633,3 +633,135 @@ int orbgpu_features_in_area(orbgpu_features *f, const orbgpu_query *queries, int
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// DBoW2 vocabulary tree descent (TemplatedVocabulary.h:1216-1258, FORB.cpp:77-100).  Half a warp per feature: at every
+// level the 16 lanes take the children in strides of 16, the lexicographic minimum of (distance, child position) is the
+// reference's strict-'<' choice.  The upper levels of the tree (k + k^2 + k^3 nodes = 35 KB of descriptors for k = 10)
+// stay in L1 / L2; the leaves are one 32-byte row each.
+namespace orbgpu {
+namespace {
+
+__global__ void __launch_bounds__(128) k_voc_transform(const int *__restrict__ childStart, const int *__restrict__ children,
+                                                        const uint4 *__restrict__ nodeDesc, const int *__restrict__ wordId,
+                                                        const uint4 *__restrict__ feat, int n, int nidLevel, int *__restrict__ words,
+                                                        int *__restrict__ nodes) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = t >> 4, sub = t & 15;
+  const unsigned mask = 0xffffu << (threadIdx.x & 16);
+  const bool live = f < n;
+  const int fi = live ? f : n - 1;
+  const uint4 a0 = feat[2 * (size_t)fi], a1 = feat[2 * (size_t)fi + 1];
+  int node = 0, level = 0, nid = nidLevel <= 0 ? 0 : -1;
+  for (;;) {
+    const int cs = childStart[node], ce = childStart[node + 1];
+    if (cs == ce) break;                                    // leaf
+    level++;
+    unsigned best = 0xffffffffu;                            // distance << 16 | child position
+    for (int c = cs + sub; c < ce; c += 16) {
+      const int id = children[c];
+      const unsigned key = ((unsigned)hamming256(a0, a1, nodeDesc + 2 * (size_t)id) << 16) | (unsigned)(c - cs);
+      best = min(best, key);
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(mask, best, o, 16));
+    node = children[cs + (int)(best & 0xffffu)];
+    if (level == nidLevel) nid = node;
+  }
+  if (live && sub == 0) {
+    words[f] = wordId[node];
+    nodes[f] = nid >= 0 ? nid : node;                      // leaf above the requested level: see include/orbgpu.h
+  }
+}
+
+}  // namespace
+}  // namespace orbgpu
+
+struct orbgpu_vocabulary {
+  int device = 0, nodes = 0, depth = 0;
+  int *dChildStart = nullptr, *dChildren = nullptr, *dWordId = nullptr;
+  uint8_t *dDesc = nullptr;
+};
+
+namespace {
+int voc_run(orbgpu_vocabulary *v, const uint4 *dFeat, int n, int levelsup, int32_t *word_ids, int32_t *node_ids, cudaStream_t s, Workspace &W) {
+  // results reuse the workspace's match buffer: [words n | nodes n]
+  int *dOut = reinterpret_cast<int *>(W.dRes[0]);
+  k_voc_transform<<<(n * 16 + 127) / 128, 128, 0, s>>>(v->dChildStart, v->dChildren, reinterpret_cast<const uint4 *>(v->dDesc), v->dWordId, dFeat, n,
+                                                      v->depth - levelsup, dOut, dOut + n);
+  count_launch();
+  ORBGPU_CUDA_CHECK(cudaGetLastError());
+  int *hOut = reinterpret_cast<int *>(W.hRes);
+  ORBGPU_CUDA_CHECK(cudaMemcpyAsync(hOut, dOut, (size_t)2 * n * sizeof(int), cudaMemcpyDeviceToHost, s));
+  ORBGPU_CUDA_CHECK(cudaStreamSynchronize(s));
+  std::memcpy(word_ids, hOut, (size_t)n * sizeof(int));
+  std::memcpy(node_ids, hOut + n, (size_t)n * sizeof(int));
+  return ORBGPU_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int orbgpu_vocabulary_create(int32_t nodes, const int32_t *child_start, const int32_t *children, const uint8_t *descriptors,
+                             const int32_t *word_id, int32_t depth_levels, int device, orbgpu_vocabulary **out) {
+  if (!out) { set_error("null output"); return ORBGPU_E_INVALID; }
+  *out = nullptr;
+  if (nodes < 1 || !child_start || !descriptors || !word_id || depth_levels < 0 || child_start[0] != 0) { set_error("bad vocabulary arguments"); return ORBGPU_E_INVALID; }
+  const int nchild = child_start[nodes];
+  if (nchild > 0 && !children) { set_error("null children"); return ORBGPU_E_INVALID; }
+  for (int i = 0; i < nodes; i++) {
+    if (child_start[i] > child_start[i + 1] || child_start[i + 1] - child_start[i] > 65535) { set_error("node %d: bad child range", i); return ORBGPU_E_INVALID; }
+    // children must come after their parent (DBoW2 appends nodes as it grows the tree): guarantees the descent terminates
+    for (int c = child_start[i]; c < child_start[i + 1]; c++)
+      if (children[c] <= i || children[c] >= nodes) { set_error("node %d: child %d out of order", i, children[c]); return ORBGPU_E_INVALID; }
+  }
+  if (orbgpu_device_count() < 1) { set_error("no CUDA device available (this library has no CPU path)"); return ORBGPU_E_CUDA; }
+  DevGuard guard(device);
+  if (!guard.ok) { set_error("cannot select device %d", device); return ORBGPU_E_CUDA; }
+  orbgpu_vocabulary *v = new orbgpu_vocabulary;
+  cudaGetDevice(&v->device);
+  v->nodes = nodes; v->depth = depth_levels;
+  cudaError_t e = cudaMalloc(&v->dChildStart, (size_t)(nodes + 1) * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&v->dChildren, (size_t)std::max(nchild, 1) * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&v->dWordId, (size_t)nodes * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&v->dDesc, (size_t)nodes * 32);
+  if (e == cudaSuccess) e = cudaMemcpy(v->dChildStart, child_start, (size_t)(nodes + 1) * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && nchild) e = cudaMemcpy(v->dChildren, children, (size_t)nchild * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(v->dWordId, word_id, (size_t)nodes * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(v->dDesc, descriptors, (size_t)nodes * 32, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { set_error("vocabulary upload failed: %s", cudaGetErrorString(e)); orbgpu_vocabulary_destroy(v); return ORBGPU_E_CUDA; }
+  *out = v;
+  return ORBGPU_OK;
+}
+
+void orbgpu_vocabulary_destroy(orbgpu_vocabulary *v) {
+  if (!v) return;
+  DevGuard guard(v->device);
+  cudaFree(v->dChildStart); cudaFree(v->dChildren); cudaFree(v->dWordId); cudaFree(v->dDesc);
+  delete v;
+}
+
+int orbgpu_vocabulary_transform(orbgpu_vocabulary *v, const uint8_t *descriptors, int n, int levelsup, int32_t *word_ids, int32_t *node_ids) {
+  if (!v || n < 0 || (n > 0 && (!descriptors || !word_ids || !node_ids))) { set_error("bad arguments"); return ORBGPU_E_INVALID; }
+  if (n == 0) return ORBGPU_OK;
+  DevGuard guard(v->device);
+  Workspace &W = t_ws;
+  cudaError_t e = ensure(W, v->device, (size_t)n * 32, (size_t)n, 0);
+  if (e != cudaSuccess) { set_error("workspace allocation failed: %s", cudaGetErrorString(e)); return ORBGPU_E_CUDA; }
+  std::memcpy(W.hStage, descriptors, (size_t)n * 32);
+  ORBGPU_CUDA_CHECK(cudaMemcpyAsync(W.dStage, W.hStage, (size_t)n * 32, cudaMemcpyHostToDevice, W.stream));
+  return voc_run(v, reinterpret_cast<const uint4 *>(W.dStage), n, levelsup, word_ids, node_ids, W.stream, W);
+}
+
+int orbgpu_vocabulary_transform_features(orbgpu_vocabulary *v, orbgpu_features *f, int levelsup, int32_t *word_ids, int32_t *node_ids) {
+  if (!v || !f || (f->n > 0 && (!word_ids || !node_ids))) { set_error("bad arguments"); return ORBGPU_E_INVALID; }
+  if (f->device != v->device) { set_error("vocabulary and feature set live on different devices"); return ORBGPU_E_INVALID; }
+  if (f->n == 0) return ORBGPU_OK;
+  DevGuard guard(v->device);
+  Workspace &W = t_ws;
+  cudaError_t e = ensure(W, v->device, 0, (size_t)f->n, 0);
+  if (e != cudaSuccess) { set_error("workspace allocation failed: %s", cudaGetErrorString(e)); return ORBGPU_E_CUDA; }
+  return voc_run(v, reinterpret_cast<const uint4 *>(f->dDesc), f->n, levelsup, word_ids, node_ids, W.stream, W);
+}
+
+}  // extern "C"

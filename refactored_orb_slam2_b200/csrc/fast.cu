@@ -16,10 +16,14 @@
 // (cp.async.bulk.tensor.3d on the level's [batch][rows][pitch] u8 tensor map, completion on an
 // mbarrier).  TMA needs the window's first column on a 16-byte boundary, so pixels are grouped by
 // fours on the PADDED plane's 4-byte grid (groups sit on 32-bit words in shared memory) and the up
-// to 3 + 3 pixels a row of groups overhangs the tile are masked out.  A thread owns 4 horizontally adjacent pixels: 21 LDS.32 fetch the 7 ring rows, PRMT
-// unpacks byte pairs into packed s16x2, and the arc margins of two pixels at a time come from the
-// 3-input VIMNMX3.S16x2 min/max of sm_100a (sliding min3-of-min3 = every 9-arc in 32 ops, 82 ops
-// per pixel pair for both polarities).  Scores (margin - minTh, 0 = not a corner at minTh) go to a
+// to 3 + 3 pixels a row of groups overhangs the tile are masked out.  The u8 window is unpacked ONCE per tile into two
+// u16 planes — plane A holds pixel pairs (2j, 2j+1) per 32-bit word, plane B the pairs (2j+1, 2j+2) — so that every ring
+// pixel pair of a thread's two adjacent pixels, at any horizontal offset, is one aligned shared-memory word that is already
+// the packed u16x2 operand of the arithmetic (no per-use PRMT / mask: the unpack costs 1 ALU op per pixel instead of ~13).
+// A thread owns 4 horizontally adjacent pixels = two such pairs: 22 LDS (64-bit where the second pair's word sits next to
+// the first's) fetch both rings and centres, and the arc margins come from the 3-input VIMNMX3.S16x2 min/max of sm_100a
+// (sliding min3-of-min3 = every 9-arc in 32 ops, 80 ops per pixel pair for both polarities).  The TMA copy of the next
+// tile is issued as soon as the unpack has released the u8 window, so it overlaps the whole margin / NMS / emit phase.  Scores (margin - minTh, 0 = not a corner at minTh) go to a
 // shared u8 tile and the coordinates of the non-zero ones to a shared queue (warp-aggregated
 // reservation); NMS and the per-cell threshold fallback run over that queue only; survivors are
 // staged in shared memory and appended to the level's candidate list with one global atomic per CTA.
@@ -41,31 +45,12 @@ __device__ __forceinline__ unsigned mn3(unsigned a, unsigned b, unsigned c) { re
 __device__ __forceinline__ unsigned mx3(unsigned a, unsigned b, unsigned c) { return __vimax3_s16x2(a, b, c); }
 __device__ __forceinline__ unsigned mx2(unsigned a, unsigned b) { return __vmaxs2(a, b); }
 
-// Bytes O, O+1 of the 12-byte window (w0, w1, w2), zero-extended into packed 16x2.
-template <int O>
-__device__ __forceinline__ unsigned pair_at(unsigned w0, unsigned w1, unsigned w2) {
-  static_assert(O >= 0 && O <= 10, "window offset");
-  if constexpr (O <= 2) return __byte_perm(w0, 0u, 0x4040u | O | ((O + 1) << 8));
-  else if constexpr (O == 3) return __byte_perm(w0, w1, 0x4443u) & 0x00ff00ffu;
-  else if constexpr (O <= 6) return __byte_perm(w1, 0u, 0x4040u | (O - 4) | ((O - 3) << 8));
-  else if constexpr (O == 7) return __byte_perm(w1, w2, 0x4443u) & 0x00ff00ffu;
-  else return __byte_perm(w2, 0u, 0x4040u | (O - 8) | ((O - 7) << 8));
-}
-
-// Arc margins (packed s16x2) of the two pixels at window bytes C, C+1; rows[r] = window words of image row y-3+r.
-// min / max commute with subtracting the centre, so the sliding-window networks run on the RAW ring pixels and the
-// centre is subtracted once from the two extrema:
+// Arc margins (packed s16x2) of two horizontally adjacent pixels from their 16 ring values d[k] (packed u16x2, ring order
+// of cv::FAST 9/16: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)) and
+// their centres c.  min / max commute with subtracting the centre, so the sliding-window networks run on the RAW ring pixels
+// and the centre is subtracted once from the two extrema:
 //   bright margin = max_arcs min_arc(ring) - centre ,  dark margin = centre - min_arcs max_arc(ring).
-template <int C>
-__device__ __forceinline__ unsigned margin_pair(const unsigned (&w)[7][3]) {
-  unsigned d[16];
-  // ring order of cv::FAST 9/16: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
-#define RING(k, dx, dy) d[k] = pair_at<C + (dx)>(w[3 + (dy)][0], w[3 + (dy)][1], w[3 + (dy)][2])
-  RING(0, 0, 3);   RING(1, 1, 3);   RING(2, 2, 2);    RING(3, 3, 1);
-  RING(4, 3, 0);   RING(5, 3, -1);  RING(6, 2, -2);   RING(7, 1, -3);
-  RING(8, 0, -3);  RING(9, -1, -3); RING(10, -2, -2); RING(11, -3, -1);
-  RING(12, -3, 0); RING(13, -3, 1); RING(14, -2, 2);  RING(15, -1, 3);
-#undef RING
+__device__ __forceinline__ unsigned margin_of_ring(const unsigned (&d)[16], unsigned c) {
   unsigned a3[16], b3[16];
 #pragma unroll
   for (int k = 0; k < 16; k++) {
@@ -82,7 +67,6 @@ __device__ __forceinline__ unsigned margin_pair(const unsigned (&w)[7][3]) {
     const unsigned b9b = mx3(b3[k + 1], b3[(k + 4) & 15], b3[(k + 7) & 15]);
     dark = mn3(dark, b9, b9b);
   }
-  const unsigned c = pair_at<C>(w[3][0], w[3][1], w[3][2]);
   return mx2(__vsub2(bright, c), __vsub2(c, dark));
 }
 
@@ -111,86 +95,122 @@ __device__ __forceinline__ TileGeom tile_geom(const LevelTable *T, const int4 *t
   return t;
 }
 
-// Persistent CTAs: each walks items blockIdx.x, blockIdx.x + gridDim.x, ... with a two-stage window ring, so the TMA
-// copy of the next tile is in flight while the current one is processed.
+// Persistent CTAs: each walks items blockIdx.x, blockIdx.x + gridDim.x, ...
 __global__ void __launch_bounds__(kThreads, 4)
 k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict__ T, const int4 *__restrict__ tiles,
              int ntiles, int totalItems, int imgBase, Cand *__restrict__ cand, int *__restrict__ candCount,
              unsigned *__restrict__ status, const FastConfig cfg) {
   extern __shared__ uint8_t smemRaw[];
-  __shared__ __align__(8) unsigned long long sBar[2];
+  __shared__ __align__(8) unsigned long long sBar;
   __shared__ int sCellCnt[kFastCellsPerTile];
   __shared__ int sEmit, sBase, sQueued, sKept, sOut;
 
   const int iniTh = T->iniTh, minTh = T->minTh;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   uint8_t *smem = smemRaw + ((128u - (smem_u32(smemRaw) & 127u)) & 127u);   // TMA destination: 128-byte aligned
+  // [u8 window: imgBytes][plane A: 2 x imgBytes][plane B: 2 x imgBytes][scores][queue]; the survivor stage list aliases
+  // plane A, which is dead once the margins are computed
+  unsigned *sPlaneA = reinterpret_cast<unsigned *>(smem + cfg.imgBytes);
+  unsigned *sPlaneB = reinterpret_cast<unsigned *>(smem + 3 * cfg.imgBytes);
   // u8 scores, pitch cfg.scorePitch, column 0 = padded column gx0; one halo row above / below (kept zero) and one halo
   // column on each side (always masked by the cell test) so that NMS reads its 8 neighbours without bounds checks
-  uint8_t *sScore = smem + 2 * cfg.imgBytes + cfg.scorePitch + 4;
-  Cand *sStage = reinterpret_cast<Cand *>(smem + 2 * cfg.imgBytes + cfg.scoreBytes);
-  unsigned short *sQueue = reinterpret_cast<unsigned short *>(sStage + cfg.stageCap);   // (row << 8 | column) of non-zero scores
+  uint8_t *sScore = smem + 5 * cfg.imgBytes + cfg.scorePitch + 4;
+  unsigned short *sQueue = reinterpret_cast<unsigned short *>(smem + 5 * cfg.imgBytes + cfg.scoreBytes);   // (row << 8 | column) of non-zero scores
+  Cand *sStage = reinterpret_cast<Cand *>(sPlaneA);
   const int sp = cfg.scorePitch;
 
   if (tid == 0) {
-    mbar_init(&sBar[0], 1);
-    mbar_init(&sBar[1], 1);
+    mbar_init(&sBar, 1);
     mbar_fence_init();
   }
   __syncthreads();
   if (tid == 0 && (int)blockIdx.x < totalItems) {
     const TileGeom n = tile_geom(T, tiles, ntiles, blockIdx.x, imgBase);
     const LevelGeom &Gn = T->lv[n.level];
-    mbar_expect_tx(&sBar[0], (unsigned)(Gn.fastBoxW * Gn.fastBoxH));
-    tma_load_3d(smem, &maps.m[n.level], n.bx, n.Y0 - 3 + kEdge, n.img, &sBar[0]);
+    mbar_expect_tx(&sBar, (unsigned)(Gn.fastBoxW * Gn.fastBoxH));
+    tma_load_3d(smem, &maps.m[n.level], n.bx, n.Y0 - 3 + kEdge, n.img, &sBar);
   }
 
   int iter = 0;
   for (int item = blockIdx.x; item < totalItems; item += gridDim.x, iter++) {
-    const int stage = iter & 1;
     const TileGeom tg = tile_geom(T, tiles, ntiles, item, imgBase);
     const LevelGeom &G = T->lv[tg.level];
     const int level = tg.level, img = tg.img, X0 = tg.X0, Y0 = tg.Y0, TW = tg.TW, TH = tg.TH;
     const int offL = tg.offL, groups = tg.groups, lead = tg.lead;
-    const uint8_t *sImg = smem + stage * cfg.imgBytes;    // fastBoxW x fastBoxH window of this item
     const int bw = G.fastBoxW;
-    if (tid == 0) {
-      sEmit = 0; sQueued = 0; sKept = 0; sOut = 0;
-      const int next = item + gridDim.x;
-      if (next < totalItems) {                            // the other stage was released by the barrier ending the last item
-        const TileGeom n = tile_geom(T, tiles, ntiles, next, imgBase);
-        const LevelGeom &Gn = T->lv[n.level];
-        mbar_expect_tx(&sBar[stage ^ 1], (unsigned)(Gn.fastBoxW * Gn.fastBoxH));
-        tma_load_3d(smem + (stage ^ 1) * cfg.imgBytes, &maps.m[n.level], n.bx, n.Y0 - 3 + kEdge, n.img, &sBar[stage ^ 1]);
-      }
-    }
+    if (tid == 0) { sEmit = 0; sQueued = 0; sKept = 0; sOut = 0; }
     if (tid < kFastCellsPerTile) sCellCnt[tid] = 0;
     for (int i = tid; i < 2 * (sp >> 2); i += kThreads) {   // zero the halo rows -1 and TH
       const int half = sp >> 2;
       unsigned *rowp = reinterpret_cast<unsigned *>(sScore + (i < half ? -1 : TH) * sp - 4);
       rowp[i < half ? i : i - half] = 0u;
     }
-    __syncthreads();
-    mbar_wait(&sBar[stage], (iter >> 1) & 1);
+    mbar_wait(&sBar, iter & 1);
+
+    // ---- unpack the u8 window into the two u16 planes (the window's rows are contiguous: word i + 1 follows word i, and the
+    // pair that straddles a row end is never read)
+    {
+      const unsigned *src = reinterpret_cast<const unsigned *>(smem);
+      uint2 *dA = reinterpret_cast<uint2 *>(sPlaneA), *dB = reinterpret_cast<uint2 *>(sPlaneB);
+      const int nwords = (bw >> 2) * (TH + 6);
+      for (int i = tid; i < nwords; i += kThreads) {
+        const unsigned w0 = src[i], w1 = src[i + 1];
+        dA[i] = make_uint2(__byte_perm(w0, 0u, 0x4140u), __byte_perm(w0, 0u, 0x4342u));
+        dB[i] = make_uint2(__byte_perm(w0, 0u, 0x4241u), __byte_perm(w0, w1, 0x4443u) & 0x00ff00ffu);
+      }
+    }
+    __syncthreads();                                       // planes complete; the u8 window and last item's stage list are free
+    if (tid == 0) {
+      const int next = item + gridDim.x;
+      if (next < totalItems) {
+        const TileGeom n = tile_geom(T, tiles, ntiles, next, imgBase);
+        const LevelGeom &Gn = T->lv[n.level];
+        mbar_expect_tx(&sBar, (unsigned)(Gn.fastBoxW * Gn.fastBoxH));
+        tma_load_3d(smem, &maps.m[n.level], n.bx, n.Y0 - 3 + kEdge, n.img, &sBar);
+      }
+    }
 
     // ---- arc margins: work items = (row, 4-pixel group) pairs, dealt round-robin to the CTA's threads so that every
     // lane is busy whatever the tile shape; corners at minTh are queued
     const unsigned th2 = (unsigned)minTh * 0x00010001u;
     const int items = TH * groups;
     const int stepY = kThreads / groups, stepG = kThreads - stepY * groups;
+    const int pw = bw >> 1;                                // plane pitch in 32-bit words
     int y = tid / groups, g = tid - y * groups;
     for (int i0 = 0; i0 < items; i0 += kThreads) {
       unsigned packed = 0;
       if (i0 + tid < items) {
-        unsigned w[7][3];
-#pragma unroll
-        for (int r = 0; r < 7; r++) {
-          const unsigned *row = reinterpret_cast<const unsigned *>(sImg + (y + r) * bw + lead) + g;
-          w[r][0] = row[0]; w[r][1] = row[1]; w[r][2] = row[2];
+        // word index of the thread's first pixel pair (window column lead + 4g + 4, always even); P = that pair, Q = the next
+        const int a = y * pw + ((lead + 4) >> 1) + 2 * g;
+        const unsigned *A = sPlaneA + a, *B = sPlaneB + a;
+        unsigned dP[16], dQ[16];
+        {   // rows y-3 / y+3 (ring 7, 8, 9 / 15, 0, 1): dx = +1, 0, -1
+          const uint2 a0 = *reinterpret_cast<const uint2 *>(A), b0 = *reinterpret_cast<const uint2 *>(B);
+          const unsigned bm = B[-1];
+          dP[8] = a0.x; dQ[8] = a0.y; dP[7] = b0.x; dQ[7] = b0.y; dP[9] = bm; dQ[9] = b0.x;
+          const uint2 a6 = *reinterpret_cast<const uint2 *>(A + 6 * pw), b6 = *reinterpret_cast<const uint2 *>(B + 6 * pw);
+          const unsigned bm6 = B[6 * pw - 1];
+          dP[0] = a6.x; dQ[0] = a6.y; dP[1] = b6.x; dQ[1] = b6.y; dP[15] = bm6; dQ[15] = b6.x;
         }
+        {   // rows y-2 / y+2 (ring 6, 10 / 2, 14): dx = +2, -2
+          const uint2 a1 = *reinterpret_cast<const uint2 *>(A + pw);
+          dP[6] = a1.y; dQ[6] = A[pw + 2]; dP[10] = A[pw - 1]; dQ[10] = a1.x;
+          const uint2 a5 = *reinterpret_cast<const uint2 *>(A + 5 * pw);
+          dP[2] = a5.y; dQ[2] = A[5 * pw + 2]; dP[14] = A[5 * pw - 1]; dQ[14] = a5.x;
+        }
+        {   // rows y-1 / y+1 (ring 5, 11 / 3, 13): dx = +3, -3
+          const uint2 b2 = *reinterpret_cast<const uint2 *>(B + 2 * pw - 2);
+          dP[5] = B[2 * pw + 1]; dQ[5] = B[2 * pw + 2]; dP[11] = b2.x; dQ[11] = b2.y;
+          const uint2 b4 = *reinterpret_cast<const uint2 *>(B + 4 * pw - 2);
+          dP[3] = B[4 * pw + 1]; dQ[3] = B[4 * pw + 2]; dP[13] = b4.x; dQ[13] = b4.y;
+        }
+        // row y (ring 4, 12): dx = +3, -3, and the centres
+        const uint2 b3 = *reinterpret_cast<const uint2 *>(B + 3 * pw - 2);
+        dP[4] = B[3 * pw + 1]; dQ[4] = B[3 * pw + 2]; dP[12] = b3.x; dQ[12] = b3.y;
+        const uint2 c = *reinterpret_cast<const uint2 *>(A + 3 * pw);
         // score = max(margin, minTh) - minTh: 0 when the pixel is not a corner at minTh
-        const unsigned sA = __vsub2(mx2(margin_pair<4>(w), th2), th2);
-        const unsigned sB = __vsub2(mx2(margin_pair<6>(w), th2), th2);
+        const unsigned sA = __vsub2(mx2(margin_of_ring(dP, c.x), th2), th2);
+        const unsigned sB = __vsub2(mx2(margin_of_ring(dQ, c.y), th2), th2);
         packed = __byte_perm(sA, sB, 0x6420u);
         // pixels of the first / last group outside the tile's detection columns
         const int lo = offL - 4 * g, hi = offL + TW - 4 * g;
@@ -268,7 +288,7 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
       if (slot < G.candCap) out[slot] = o;
     }
   }
-    __syncthreads();   // stage list, queue, counters and this item's window are free again
+    __syncthreads();   // stage list (= plane A), queue and counters are free again
   }
 }
 
@@ -287,12 +307,14 @@ FastConfig fast_make_config(const LevelTable &T) {
   }
   FastConfig c;
   const int tw = kFastCellsPerTile * wMax;
-  c.imgBytes = (img + 127) & ~127;
+  c.imgBytes = (img + 4 + 127) & ~127;               // + the word the unpack reads past the last one
   c.scorePitch = (tw + 3 + 3 + 3) & ~3;             // + the group overhang on both sides
   c.scoreBytes = (c.scorePitch * (hMax + 2) + 8 + 15) & ~15;   // + halo rows and the 4-byte lead of the halo column
   c.stageCap = (tw / 2 + 1) * (hMax / 2 + 1);      // bound on strict 8-neighbour maxima in a tile
   c.queueCap = c.scorePitch * hMax;
-  c.smemBytes = 128 + 2 * c.imgBytes + c.scoreBytes + c.stageCap * (int)sizeof(Cand) + c.queueCap * 2;
+  // window + two u16 planes (the stage list lives in plane A) + scores + queue
+  if (c.stageCap * (int)sizeof(Cand) > 2 * c.imgBytes) c.stageCap = 2 * c.imgBytes / (int)sizeof(Cand);
+  c.smemBytes = 128 + 5 * c.imgBytes + c.scoreBytes + c.queueCap * 2;
   c.maxIters = ((hMax + kWarps - 1) / kWarps) * (((tw + 6 + 3) / 4 + 31) / 32);
   return c;
 }

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORBGPU_VERSION 120
+#define ORBGPU_VERSION 130
 
 enum {
   ORBGPU_OK = 0,
@@ -315,6 +315,31 @@ int orbgpu_vocabulary_transform(orbgpu_vocabulary *v, const uint8_t *descriptors
 /* The same for the descriptors of a device-resident feature set (no upload). */
 int orbgpu_vocabulary_transform_features(orbgpu_vocabulary *v, orbgpu_features *f, int levelsup, int32_t *word_ids,
                                          int32_t *node_ids);
+
+/* ------------------------------------------------------------------------------------------------
+ * Input staging: what the reference does to an image right before
+ * the extractor sees it, on the device, so colour / unrectified frames need only one H2D.
+ *   cvtColor(…, COLOR_{RGB,BGR,RGBA,BGRA}2GRAY)   src/Tracking.cc:166-182, 200-211, 228-236
+ *   cv::remap(im, imRect, M1, M2, INTER_LINEAR)    Source/Examples/Stereo/stereo_euroc.cc:159-160
+ *     (M1 / M2 = CV_32F maps of cv::initUndistortRectifyMap, :109-111, computed once on the host)
+ * Arithmetic (OpenCV's, pinned bit-exact against cv2 4.13.0 in tests/test_staging.py):
+ *   gray  = (B*3735 + G*19235 + R*9798 + 2^14) >> 15
+ *   remap: sx = cvRound(mapx*32), ix = sx >> 5, fx = sx & 31 (same in y); weights (32-fx)(32-fy)*32, …
+ *          out = (sum w*p + 2^14) >> 15, taps outside the source read 0 (BORDER_CONSTANT).
+ * All pointers are DEVICE pointers; `stream` is a cudaStream_t (NULL = the legacy default stream).
+ * Images are [batch] planes `*_img_step` bytes apart with `*_step` bytes per row.
+ * ------------------------------------------------------------------------------------------------ */
+enum { ORBGPU_BGR2GRAY = 0, ORBGPU_RGB2GRAY = 1 };   /* 4-channel input: the alpha byte is ignored */
+int orbgpu_cvt_gray_device(const uint8_t *d_src, int channels, int code, int width, int height, size_t src_step,
+                           size_t src_img_step, uint8_t *d_dst, size_t dst_step, size_t dst_img_step, int batch,
+                           void *stream);
+int orbgpu_remap_device(const uint8_t *d_src, int src_width, int src_height, size_t src_step, size_t src_img_step,
+                        const float *d_map_x, const float *d_map_y, int width, int height, uint8_t *d_dst,
+                        size_t dst_step, size_t dst_img_step, int batch, void *stream);
+/* Host-buffer conveniences (upload, run, download; contiguous images). */
+int orbgpu_cvt_gray(const uint8_t *src, int channels, int code, int width, int height, uint8_t *dst, int batch, int device);
+int orbgpu_remap(const uint8_t *src, int src_width, int src_height, const float *map_x, const float *map_y, int width,
+                 int height, uint8_t *dst, int batch, int device);
 
 /* Measured integer-pipe peak (register-resident POPC loop): returns POPC lane-ops per second. */
 int orbgpu_measure_popc_peak(int device, double *popc_per_second, double *lop3_per_second);

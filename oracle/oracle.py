@@ -75,6 +75,8 @@ def lib():
         L.orb_oracle_features_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orb_oracle_features_in_area.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.orb_oracle_voc_transform.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orb_oracle_cvt_gray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orb_oracle_remap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orb_oracle_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
@@ -307,3 +309,20 @@ def voc_transform(child_start, children, node_desc, word_id, depth_levels, featu
     rc = lib().orb_oracle_voc_transform(len(wi), _p(cs), _p(ch), _p(nd), _p(wi), int(depth_levels), _p(f), len(f), int(levelsup), _p(words), _p(nodes))
     assert rc == 0
     return words, nodes
+
+
+def cvt_gray(img, code):
+    """Restated cvtColor(BGR/RGB[A] -> GRAY) for one image [H, W, 3|4]; code 0 = BGR order, 1 = RGB order."""
+    a = np.ascontiguousarray(img, np.uint8)
+    out = np.empty(a.shape[:2], np.uint8)
+    lib().orb_oracle_cvt_gray(_p(a), a.shape[2], int(code), a.shape[1], a.shape[0], _p(out))
+    return out
+
+
+def remap(img, map_x, map_y):
+    """Restated cv::remap(INTER_LINEAR, BORDER_CONSTANT 0) with float32 maps."""
+    a = np.ascontiguousarray(img, np.uint8)
+    mx, my = np.ascontiguousarray(map_x, np.float32), np.ascontiguousarray(map_y, np.float32)
+    out = np.empty(mx.shape, np.uint8)
+    lib().orb_oracle_remap(_p(a), a.shape[1], a.shape[0], _p(mx), _p(my), mx.shape[1], mx.shape[0], _p(out))
+    return out

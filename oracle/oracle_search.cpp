@@ -275,3 +275,28 @@ extern "C" int orb_oracle_voc_transform(int nodes, const int32_t *childStart, co
   }
   return ORBGPU_OK;
 }
+
+// ---- input staging: OpenCV's fixed-point cvtColor(*2GRAY) and remap(INTER_LINEAR, BORDER_CONSTANT) ----
+// Call sites: src/Tracking.cc:166-182 (cvtColor), Examples/Stereo/stereo_euroc.cc:159-160 (remap).  OpenCV is not under
+// /root/reference; both restatements are pinned bit-exact against cv2 4.13.0 by tests/test_staging.py.
+extern "C" void orb_oracle_cvt_gray(const uint8_t *src, int channels, int code, int width, int height, uint8_t *dst) {
+  const int c0 = code == ORBGPU_RGB2GRAY ? 9798 : 3735, c2 = code == ORBGPU_RGB2GRAY ? 3735 : 9798;
+  for (size_t i = 0; i < (size_t)width * height; i++) {
+    const uint8_t *p = src + i * channels;
+    dst[i] = (uint8_t)((p[0] * c0 + p[1] * 19235 + p[2] * c2 + (1 << 14)) >> 15);
+  }
+}
+
+extern "C" void orb_oracle_remap(const uint8_t *src, int sw, int sh, const float *mapX, const float *mapY, int width, int height, uint8_t *dst) {
+  for (int y = 0; y < height; y++)
+    for (int x = 0; x < width; x++) {
+      const size_t m = (size_t)y * width + x;
+      const int sx = (int)lrintf(mapX[m] * 32.f), sy = (int)lrintf(mapY[m] * 32.f);      // cvRound(v * INTER_TAB_SIZE)
+      const int fx = sx & 31, fy = sy & 31;
+      const int ix = std::max(-32768, std::min(32767, sx >> 5)), iy = std::max(-32768, std::min(32767, sy >> 5));
+      auto tap = [&](int yy, int xx) -> int { return (xx >= 0 && xx < sw && yy >= 0 && yy < sh) ? src[(size_t)yy * sw + xx] : 0; };
+      const int v = (32 - fx) * (32 - fy) * 32 * tap(iy, ix) + fx * (32 - fy) * 32 * tap(iy, ix + 1) + (32 - fx) * fy * 32 * tap(iy + 1, ix) +
+                    fx * fy * 32 * tap(iy + 1, ix + 1);
+      dst[m] = (uint8_t)((v + (1 << 14)) >> 15);
+    }
+}

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128) k_remap(const uint8_t *__restrict__ src, 
   const size_t m = (size_t)y * width + x4;
   const int n = min(4, width - x4);
   float mx[4], my[4];
-  if (n == 4 && (m & 3) == 0) {
+  if (n == 4 && ((((uintptr_t)(mapX + m)) | ((uintptr_t)(mapY + m))) & 15) == 0) {
     const float4 a = *reinterpret_cast<const float4 *>(mapX + m), b = *reinterpret_cast<const float4 *>(mapY + m);
     mx[0] = a.x; mx[1] = a.y; mx[2] = a.z; mx[3] = a.w; my[0] = b.x; my[1] = b.y; my[2] = b.z; my[3] = b.w;
   } else {

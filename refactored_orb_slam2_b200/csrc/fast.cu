@@ -103,7 +103,7 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
   extern __shared__ uint8_t smemRaw[];
   __shared__ __align__(8) unsigned long long sBar;
   __shared__ int sCellCnt[kFastCellsPerTile];
-  __shared__ int sEmit, sBase, sQueued, sKept, sOut;
+  __shared__ int sQueued, sKept;
 
   const int iniTh = T->iniTh, minTh = T->minTh;
   const int tid = threadIdx.x;
@@ -138,7 +138,7 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
     const int level = tg.level, img = tg.img, X0 = tg.X0, Y0 = tg.Y0, TW = tg.TW, TH = tg.TH;
     const int offL = tg.offL, groups = tg.groups, lead = tg.lead;
     const int bw = G.fastBoxW;
-    if (tid == 0) { sEmit = 0; sQueued = 0; sKept = 0; sOut = 0; }
+    if (tid == 0) { sQueued = 0; sKept = 0; }
     if (tid < kFastCellsPerTile) sCellCnt[tid] = 0;
     for (int i = tid; i < 2 * (sp >> 2); i += kThreads) {   // zero the halo rows -1 and TH
       const int half = sp >> 2;
@@ -263,29 +263,33 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
   }
   __syncthreads();
 
-  // ---- emit: cells with no survivor at iniTh fall back to minTh (ORBextractor.cc:776-780)
+  // ---- emit: cells with no survivor at iniTh fall back to minTh (ORBextractor.cc:776-780).  Every warp appends its share
+  // of the stage list on its own: ballot, one global atomic per warp round, no CTA-wide barrier on the critical path.
   const int nk = min(sKept, cfg.stageCap);
   if (tid == 0 && sKept > cfg.stageCap) atomicOr(status, kStatusCandOverflow);
-  int myEmit = 0;
-  for (int i = tid; i < nk; i += kThreads) {
-    const Cand o = sStage[i];
-    const int s = (int)(o.resp & 0xffffu) + 1 - minTh, c = (int)(o.resp >> 16);
-    myEmit += (s > iniS || sCellCnt[c] == 0) ? 1 : 0;
-  }
-  if (myEmit) atomicAdd(&sEmit, myEmit);
-  __syncthreads();
-  if (tid == 0) sBase = sEmit > 0 ? atomicAdd(&candCount[img * kMaxLevels + level], sEmit) : 0;
-  __syncthreads();
-  const int base = sBase;
-  if (tid == 0 && base + sEmit > G.candCap) atomicOr(status, kStatusCandOverflow);
-  Cand *out = cand + G.candOffset + (size_t)img * G.candCap;
-  for (int i = tid; i < nk; i += kThreads) {
-    Cand o = sStage[i];
-    const int s = (int)(o.resp & 0xffffu) + 1 - minTh, c = (int)(o.resp >> 16);
-    if (s > iniS || sCellCnt[c] == 0) {
-      const int slot = base + atomicAdd(&sOut, 1);
-      o.resp &= 0xffffu;
-      if (slot < G.candCap) out[slot] = o;
+  {
+    const int lane = tid & 31;
+    int *counter = &candCount[img * kMaxLevels + level];
+    Cand *out = cand + G.candOffset + (size_t)img * G.candCap;
+    for (int i0 = (tid >> 5) * 32; i0 < nk; i0 += kThreads) {
+      const int i = i0 + lane;
+      Cand o;
+      bool emit = false;
+      if (i < nk) {
+        o = sStage[i];
+        const int s = (int)(o.resp & 0xffffu) + 1 - minTh, c = (int)(o.resp >> 16);
+        emit = s > iniS || sCellCnt[c] == 0;
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, emit);
+      if (mask == 0u) continue;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(counter, __popc(mask));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (emit) {
+        const int slot = base + __popc(mask & ((1u << lane) - 1u));
+        o.resp &= 0xffffu;
+        if (slot < G.candCap) out[slot] = o; else atomicOr(status, kStatusCandOverflow);
+      }
     }
   }
     __syncthreads();   // stage list (= plane A), queue and counters are free again

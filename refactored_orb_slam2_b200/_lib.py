@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liborbgpu.so")
+LIB_PATH = os.environ.get("ORBGPU_LIB") or os.path.join(_HERE, "liborbgpu.so")    # ORBGPU_LIB: tuning builds (tools/)
 
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_UNSUPPORTED = 0, -1, -2, -3, -4
 

@@ -38,7 +38,7 @@ namespace orbgpu {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = ORBGPU_FAST_THREADS;
 constexpr int kWarps = kThreads / 32;
 
 __device__ __forceinline__ unsigned mn3(unsigned a, unsigned b, unsigned c) { return __vimin3_s16x2(a, b, c); }
@@ -96,7 +96,7 @@ __device__ __forceinline__ TileGeom tile_geom(const LevelTable *T, const int4 *t
 }
 
 // Persistent CTAs: each walks items blockIdx.x, blockIdx.x + gridDim.x, ...
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, ORBGPU_FAST_CTAS_PER_SM)
 k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict__ T, const int4 *__restrict__ tiles,
              int ntiles, int totalItems, int imgBase, Cand *__restrict__ cand, int *__restrict__ candCount,
              unsigned *__restrict__ status, const FastConfig cfg) {
@@ -329,7 +329,7 @@ cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const TmaM
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  static const int ctasPerSm = [] { const char *e = getenv("ORBGPU_FAST_CTAS"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 4 ? v : 4; }();
+  static const int ctasPerSm = [] { const char *e = getenv("ORBGPU_FAST_CTAS"); const int v = e ? atoi(e) : ORBGPU_FAST_CTAS_PER_SM; return v >= 1 && v <= ORBGPU_FAST_CTAS_PER_SM ? v : ORBGPU_FAST_CTAS_PER_SM; }();
   const int grid = total < ctasPerSm * sms ? total : ctasPerSm * sms;
   k_fast_cells<<<grid, kThreads, c.smemBytes, s>>>(maps, B.dT, tiles, ntiles, total, imgBase, B.cand, B.candCount, B.status, c);
   count_launch();

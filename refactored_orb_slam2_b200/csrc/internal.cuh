@@ -118,7 +118,16 @@ int blur_box_h();
 int blur_smem_bytes();
 cudaError_t blur_configure();
 void blur_make_tiles(const LevelTable &T, std::vector<int4> &tiles);
-constexpr int kFastCellsPerTile = 4;
+#ifndef ORBGPU_FAST_CELLS
+#define ORBGPU_FAST_CELLS 4
+#endif
+#ifndef ORBGPU_FAST_THREADS
+#define ORBGPU_FAST_THREADS 256
+#endif
+#ifndef ORBGPU_FAST_CTAS_PER_SM
+#define ORBGPU_FAST_CTAS_PER_SM 4
+#endif
+constexpr int kFastCellsPerTile = ORBGPU_FAST_CELLS;
 struct FastConfig { int imgBytes, scorePitch, scoreBytes, stageCap, queueCap, smemBytes, maxIters; };
 FastConfig fast_make_config(const LevelTable &T);
 cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &maps, const int4 *tiles, int ntiles,

@@ -280,7 +280,7 @@ def run_own(args, rank, local_rank, world):
         step_e2e()
     torch.cuda.synchronize()
     dt_sync = max_over_ranks(time.perf_counter() - t0)
-    # the same calls, two batches in flight (pkg.StereoBatchPipeline: two handles driven from two host threads), so that one
+    # the same calls, two batches in flight (pkg.StereoBatchPipeline: two handles, split async / wait entry points, one host thread), so that one
     # batch uploads while the other computes; every batch is copied in from pinned host memory and its results copied out
     del out_k, out_d, out_c, out_u, out_z
     pipe = pkg.StereoBatchPipeline(PARAMS, W, H, pairs, BF, mb, depth=2, device=local_rank)
@@ -291,9 +291,10 @@ def run_own(args, rank, local_rank, world):
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
+        if i >= 2:
+            pipe.result()          # batch i - 2: frees its handle; batch i - 1 is still in flight while batch i is enqueued
         pipe.submit(host)
-        if i >= 1:
-            pipe.result()
+    pipe.result()
     last = pipe.result()
     torch.cuda.synchronize()
     dt = max_over_ranks(time.perf_counter() - t0)
@@ -406,7 +407,7 @@ def run_own(args, rank, local_rank, world):
                        "host_numa_node_rank0": numa_node},
             "clocks": clocks,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "StereoBatchPipeline(depth=2) over orbgpu_extract_batch + orbgpu_stereo_match, pinned host buffers",
+                    "api": "StereoBatchPipeline(depth=2) over orbgpu_extract_batch_async + orbgpu_stereo_match_async + orbgpu_wait, pinned host buffers",
                     "single_call_value": world * nimg * args.steps / dt_sync},
             "gpu_launches": launches,
             "stage_ms": stages,

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORBGPU_VERSION 130
+#define ORBGPU_VERSION 140
 
 enum {
   ORBGPU_OK = 0,
@@ -92,6 +92,16 @@ int orbgpu_extract_batch(orbgpu_extractor *e, const uint8_t *images, int count, 
                          size_t row_step, size_t image_step, orbgpu_keypoint *keypoints,
                          uint8_t *descriptors, int capacity, int32_t *counts);
 
+/* Split form for callers that keep several batches in flight on several handles from ONE host thread
+ * (refactored_orb_slam2_b200/pipeline.py): _async enqueues the chunked H2D copies, the kernels and the D2H copies and
+ * returns; orbgpu_wait blocks until everything queued on the handle (including an orbgpu_stereo_match_async) has
+ * landed in the host buffers, then reports device-side overflow and counts[i] > capacity.  Host buffers should be
+ * pinned, and must stay valid until orbgpu_wait returns.  orbgpu_extract_batch == _async + orbgpu_wait. */
+int orbgpu_extract_batch_async(orbgpu_extractor *e, const uint8_t *images, int count, int width, int height,
+                               size_t row_step, size_t image_step, orbgpu_keypoint *keypoints,
+                               uint8_t *descriptors, int capacity, int32_t *counts);
+int orbgpu_wait(orbgpu_extractor *e);
+
 /* Device-resident form: images already in HBM; results stay in the handle's device buffers (see
  * orbgpu_results_device) until the next extract call.  Asynchronous on the handle's stream. */
 int orbgpu_extract_batch_device(orbgpu_extractor *e, const uint8_t *d_images, int count, int width,
@@ -132,6 +142,9 @@ int orbgpu_get_blurred_level(orbgpu_extractor *e, int image, int level, uint8_t 
 int orbgpu_stereo_match(orbgpu_extractor *left, orbgpu_extractor *right, int first_left,
                         int first_right, int pairs, float mbf, float mb, float *u_right, float *depth,
                         int capacity);
+/* The same without the final synchronisation (pair it with orbgpu_wait on `left`). */
+int orbgpu_stereo_match_async(orbgpu_extractor *left, orbgpu_extractor *right, int first_left, int first_right,
+                              int pairs, float mbf, float mb, float *u_right, float *depth, int capacity);
 /* Device-resident form; results at orbgpu_stereo_results_device of the LEFT handle. */
 int orbgpu_stereo_match_device(orbgpu_extractor *left, orbgpu_extractor *right, int first_left,
                                int first_right, int pairs, float mbf, float mb);

@@ -65,6 +65,8 @@ SYMBOLS = {
     "orbgpu_extractor_capacity": (_i, [_vp]),
     "orbgpu_extract": (_i, [_vp, _vp, _i, _i, _sz, _vp, _vp, _i, C.POINTER(_i)]),
     "orbgpu_extract_batch": (_i, [_vp, _vp, _i, _i, _i, _sz, _sz, _vp, _vp, _i, _vp]),
+    "orbgpu_extract_batch_async": (_i, [_vp, _vp, _i, _i, _i, _sz, _sz, _vp, _vp, _i, _vp]),
+    "orbgpu_wait": (_i, [_vp]),
     "orbgpu_extract_batch_device": (_i, [_vp, _vp, _i, _i, _i, _sz, _sz]),
     "orbgpu_results_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i)]),
     "orbgpu_download_results": (_i, [_vp, _vp, _vp, _i, _vp]),
@@ -75,6 +77,7 @@ SYMBOLS = {
     "orbgpu_get_stage": (_i, [_vp, _i, _i, _i, _vp, _i]),
     "orbgpu_get_blurred_level": (_i, [_vp, _i, _i, _vp, _sz]),
     "orbgpu_stereo_match": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _i]),
+    "orbgpu_stereo_match_async": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _i]),
     "orbgpu_stereo_match_device": (_i, [_vp, _vp, _i, _i, _i, _f, _f]),
     "orbgpu_stereo_results_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "orbgpu_descriptor_distance": (_i, [_vp, _vp, _i, _vp, _i]),

@@ -89,6 +89,8 @@ struct orbgpu_extractor {
   float *dURight = nullptr, *dDepth = nullptr; int *dBestSad = nullptr, *dRowStart = nullptr, *dSorted = nullptr;
   cudaEvent_t evDone = nullptr;
   int lastBatch = 0;
+  // outputs of an enqueued, not yet awaited host-buffer batch (orbgpu_extract_batch_async .. orbgpu_wait)
+  const int32_t *pendingCounts = nullptr; int pendingCount = 0, pendingCapacity = 0;
   // host-buffer pipeline: copy streams + per-chunk events
   static constexpr int kMaxChunks = 16;
   cudaStream_t copyIn = nullptr, copyOut = nullptr;
@@ -587,8 +589,8 @@ int orbgpu_download_results(orbgpu_extractor *e, orbgpu_keypoint *keypoints, uin
 
 // Host-buffer form.  Large batches are cut into chunks that flow through three streams — H2D copy, the kernel
 // sequence, D2H copy — so that the PCIe transfers of chunks k+1 / k-1 overlap the kernels of chunk k.
-int orbgpu_extract_batch(orbgpu_extractor *e, const uint8_t *images, int count, int width, int height, size_t row_step,
-                         size_t image_step, orbgpu_keypoint *keypoints, uint8_t *descriptors, int capacity, int32_t *counts) {
+int orbgpu_extract_batch_async(orbgpu_extractor *e, const uint8_t *images, int count, int width, int height, size_t row_step,
+                               size_t image_step, orbgpu_keypoint *keypoints, uint8_t *descriptors, int capacity, int32_t *counts) {
   if (!e || !images || !counts) { set_error("null argument"); return ORBGPU_E_INVALID; }
   if (count < 1 || count > e->p.max_batch) { set_error("batch %d outside 1..%d", count, e->p.max_batch); return ORBGPU_E_CAPACITY; }
   if (width < 1 || height < 1 || row_step < (size_t)width) { set_error("bad image shape"); return ORBGPU_E_INVALID; }
@@ -651,12 +653,29 @@ int orbgpu_extract_batch(orbgpu_extractor *e, const uint8_t *images, int count, 
     }
   }
   e->lastBatch = count;
-  ORBGPU_CUDA_CHECK(cudaStreamSynchronize(e->copyOut));
-  rc = check_status(e);
+  e->pendingCounts = counts; e->pendingCount = count; e->pendingCapacity = capacity;
+  return ORBGPU_OK;
+}
+
+int orbgpu_wait(orbgpu_extractor *e) {
+  if (!e) { set_error("null handle"); return ORBGPU_E_INVALID; }
+  DeviceGuard guard(e->device);
+  if (e->copyOut) ORBGPU_CUDA_CHECK(cudaStreamSynchronize(e->copyOut));
+  int rc = check_status(e);      // synchronises the handle's stream (stereo results are copied on it)
+  const int32_t *counts = e->pendingCounts;
+  const int n = e->pendingCount, capacity = e->pendingCapacity;
+  e->pendingCounts = nullptr; e->pendingCount = 0;
   if (rc) return rc;
-  for (int i = 0; i < count; i++)
+  for (int i = 0; counts && i < n; i++)
     if (counts[i] > capacity) { set_error("capacity %d < %d keypoints", capacity, counts[i]); return ORBGPU_E_CAPACITY; }
   return ORBGPU_OK;
+}
+
+int orbgpu_extract_batch(orbgpu_extractor *e, const uint8_t *images, int count, int width, int height, size_t row_step,
+                         size_t image_step, orbgpu_keypoint *keypoints, uint8_t *descriptors, int capacity, int32_t *counts) {
+  int rc = orbgpu_extract_batch_async(e, images, count, width, height, row_step, image_step, keypoints, descriptors, capacity, counts);
+  if (rc) return rc;
+  return orbgpu_wait(e);
 }
 
 int orbgpu_extract(orbgpu_extractor *e, const uint8_t *image, int width, int height, size_t step, orbgpu_keypoint *keypoints,
@@ -787,8 +806,8 @@ int orbgpu_stereo_results_device(orbgpu_extractor *L, const float **d_u_right, c
   return ORBGPU_OK;
 }
 
-int orbgpu_stereo_match(orbgpu_extractor *L, orbgpu_extractor *R, int first_left, int first_right, int pairs, float mbf,
-                        float mb, float *u_right, float *depth, int capacity) {
+int orbgpu_stereo_match_async(orbgpu_extractor *L, orbgpu_extractor *R, int first_left, int first_right, int pairs, float mbf,
+                              float mb, float *u_right, float *depth, int capacity) {
   if (!u_right || !depth) { set_error("null output"); return ORBGPU_E_INVALID; }
   int rc = orbgpu_stereo_match_device(L, R, first_left, first_right, pairs, mbf, mb);
   if (rc) return rc;
@@ -798,6 +817,14 @@ int orbgpu_stereo_match(orbgpu_extractor *L, orbgpu_extractor *R, int first_left
                                       cudaMemcpyDeviceToHost, L->stream));
   ORBGPU_CUDA_CHECK(cudaMemcpy2DAsync(depth, (size_t)capacity * 4, L->dDepth, (size_t)L->kpCap * 4, (size_t)cols * 4, pairs,
                                       cudaMemcpyDeviceToHost, L->stream));
+  return ORBGPU_OK;
+}
+
+int orbgpu_stereo_match(orbgpu_extractor *L, orbgpu_extractor *R, int first_left, int first_right, int pairs, float mbf,
+                        float mb, float *u_right, float *depth, int capacity) {
+  int rc = orbgpu_stereo_match_async(L, R, first_left, first_right, pairs, mbf, mb, u_right, depth, capacity);
+  if (rc) return rc;
+  DeviceGuard guard(L->device);
   return check_status(L);
 }
 

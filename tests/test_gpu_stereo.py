@@ -68,7 +68,7 @@ def test_integer_shift_recovers_disparity(pkg):
 
 
 def test_pipeline_equals_sequential_calls(pkg):
-    """StereoBatchPipeline (two handles, two host threads, batches in flight) returns exactly what sequential
+    """StereoBatchPipeline (two handles, async entry points + orbgpu_wait, batches in flight) returns exactly what sequential
     extract_batch + ComputeStereoMatches calls return."""
     npairs, params = 3, (1200, 1.2, 8, 20, 7)
     bf, fx = EUROC

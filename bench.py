@@ -300,6 +300,26 @@ def run_own(args, rank, local_rank, world):
     dt = max_over_ranks(time.perf_counter() - t0)
     kmax = int(last[2].max())
     pipe.close()
+    # ---- the reference's own calling pattern: ONE stereo pair per call (configs[1] as Tracking::GrabImageStereo runs it);
+    # informational, the small-batch path replays a CUDA graph of the 13-kernel extraction sequence
+    latency_ms = None
+    if rank == 0:
+        ex1 = pkg.ORBextractor(*PARAMS, max_width=W, max_height=H, max_batch=2, device=local_rank)
+        cap1 = ex1.capacity
+        pair = torch.stack([host[0], host[pairs]]).pin_memory()
+        o = [torch.empty((2, cap1, 28), dtype=torch.uint8).pin_memory(), torch.empty((2, cap1, 32), dtype=torch.uint8).pin_memory(),
+             torch.empty(2, dtype=torch.int32).pin_memory(), torch.empty((1, cap1), dtype=torch.float32).pin_memory(),
+             torch.empty((1, cap1), dtype=torch.float32).pin_memory()]
+        ts = []
+        for i in range(60):
+            t1 = time.perf_counter()
+            pkg._lib.check(lib.orbgpu_extract_batch(ex1.handle, vp(pair.data_ptr()), 2, W, H, W, W * H, vp(o[0].data_ptr()), vp(o[1].data_ptr()), cap1,
+                                                    vp(o[2].data_ptr())))
+            pkg._lib.check(lib.orbgpu_stereo_match(ex1.handle, ex1.handle, 0, 1, 1, BF, mb, vp(o[3].data_ptr()), vp(o[4].data_ptr()), cap1))
+            if i >= 10:
+                ts.append(time.perf_counter() - t1)
+        latency_ms = float(np.median(ts) * 1e3)
+        del ex1
     e2e_fps = world * nimg * args.steps / dt
     clocks = sampler.stop() if rank == 0 else None
     h2d = nimg * W * H
@@ -408,6 +428,7 @@ def run_own(args, rank, local_rank, world):
             "clocks": clocks,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "StereoBatchPipeline(depth=2) over orbgpu_extract_batch_async + orbgpu_stereo_match_async + orbgpu_wait, pinned host buffers",
+                    "single_pair_latency_ms": latency_ms,
                     "single_call_value": world * nimg * args.steps / dt_sync},
             "gpu_launches": launches,
             "stage_ms": stages,

@@ -89,6 +89,13 @@ struct orbgpu_extractor {
   float *dURight = nullptr, *dDepth = nullptr; int *dBestSad = nullptr, *dRowStart = nullptr, *dSorted = nullptr;
   cudaEvent_t evDone = nullptr;
   int lastBatch = 0;
+  // CUDA graph of the extraction kernel sequence for small batches (the frame-at-a-time path is launch bound: 13 kernels
+  // and 2 memsets for one stereo pair); re-captured whenever its key changes
+  struct ExtractGraph {
+    cudaGraphExec_t exec = nullptr;
+    const uint8_t *dImages = nullptr; int imgBase = -1, batch = 0, w = 0, h = 0; size_t rowStep = 0, imgStep = 0;
+    int launches = 0;
+  } graph;
   // outputs of an enqueued, not yet awaited host-buffer batch (orbgpu_extract_batch_async .. orbgpu_wait)
   const int32_t *pendingCounts = nullptr; int pendingCount = 0, pendingCapacity = 0;
   // host-buffer pipeline: copy streams + per-chunk events
@@ -338,6 +345,41 @@ int run_extract_range(orbgpu_extractor *e, const uint8_t *dImages, int imgBase, 
   return ORBGPU_OK;
 }
 
+// Small batches replay a captured CUDA graph of run_extract_range instead of re-launching its kernels one by one.
+constexpr int kGraphMaxBatch = 8;
+int run_extract_range_graphed(orbgpu_extractor *e, const uint8_t *dImages, int imgBase, int batch, size_t rowStep, size_t imgStep) {
+  static const bool disabled = getenv("ORBGPU_NO_GRAPH") != nullptr;
+  if (disabled || e->profiling || batch > kGraphMaxBatch) return run_extract_range(e, dImages, imgBase, batch, rowStep, imgStep);
+  orbgpu_extractor::ExtractGraph &G = e->graph;
+  const bool hit = G.exec && G.dImages == dImages && G.imgBase == imgBase && G.batch == batch && G.w == e->cfgW && G.h == e->cfgH &&
+                   G.rowStep == rowStep && G.imgStep == imgStep;
+  if (!hit) {
+    if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+    const long long before = g_launches;
+    if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      return run_extract_range(e, dImages, imgBase, batch, rowStep, imgStep);
+    }
+    const int rc = run_extract_range(e, dImages, imgBase, batch, rowStep, imgStep);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+    const int captured = (int)(g_launches - before);
+    g_launches = before;                                   // nothing has run yet
+    if (rc != ORBGPU_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&G.exec, graph, 0) != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      G.exec = nullptr;
+      cudaGetLastError();
+      return run_extract_range(e, dImages, imgBase, batch, rowStep, imgStep);
+    }
+    cudaGraphDestroy(graph);
+    G.dImages = dImages; G.imgBase = imgBase; G.batch = batch; G.w = e->cfgW; G.h = e->cfgH; G.rowStep = rowStep; G.imgStep = imgStep;
+    G.launches = captured;
+  }
+  ORBGPU_CUDA_CHECK(cudaGraphLaunch(G.exec, e->stream));
+  count_launch(G.launches);
+  return ORBGPU_OK;
+}
+
 void begin_batch(orbgpu_extractor *e) {
   if (e->profiling) {
     e->profSlot = (int)(e->profCount++ % orbgpu_extractor::kProfRing);
@@ -350,7 +392,7 @@ int run_extract(orbgpu_extractor *e, const uint8_t *dImages, int batch, int w, i
   if (rc) return rc;
   begin_batch(e);
   ORBGPU_CUDA_CHECK(cudaMemsetAsync(e->dStatus, 0, sizeof(unsigned), e->stream));
-  rc = run_extract_range(e, dImages, 0, batch, rowStep, imgStep);
+  rc = run_extract_range_graphed(e, dImages, 0, batch, rowStep, imgStep);
   if (rc) return rc;
   e->lastBatch = batch;
   return ORBGPU_OK;
@@ -475,6 +517,7 @@ void orbgpu_extractor_destroy(orbgpu_extractor *e) {
   void *ptrs[] = {e->dT, e->dTabs, e->dTiles, e->dBlurTiles, e->dRzTiles, e->dInput, e->dPyr, e->dBlur, e->dCand, e->dNodeOf, e->dSel, e->dCandCount,
                   e->dSelCount, e->dKpCount, e->dKps, e->dDesc, e->dStatus, e->dURight, e->dDepth, e->dBestSad, e->dRowStart, e->dSorted};
   for (void *q : ptrs) if (q) cudaFree(q);
+  if (e->graph.exec) cudaGraphExecDestroy(e->graph.exec);
   if (e->evDone) cudaEventDestroy(e->evDone);
   for (cudaEvent_t ev : e->evChunkIn) if (ev) cudaEventDestroy(ev);
   for (cudaEvent_t ev : e->evChunkDone) if (ev) cudaEventDestroy(ev);
@@ -637,7 +680,7 @@ int orbgpu_extract_batch_async(orbgpu_extractor *e, const uint8_t *images, int c
     ORBGPU_CUDA_CHECK(cudaEventRecord(e->evChunkIn[c], e->copyIn));
     // ---- kernels
     ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->evChunkIn[c], 0));
-    rc = run_extract_range(e, e->dInput, first, n, width, imgBytes);
+    rc = run_extract_range_graphed(e, e->dInput, first, n, width, imgBytes);
     if (rc) return rc;
     ORBGPU_CUDA_CHECK(cudaEventRecord(e->evChunkDone[c], e->stream));
     // ---- D2H: whole rows of the chunk (counts are only known on the device; unused rows are unspecified)

@@ -9,9 +9,10 @@ A step = one pass of the hot path over one batch of synthetic KITTI-shaped stere
 (BASELINE.json configs[1]: 1241x376, nFeatures 2000, extraction of both images +
 Frame::ComputeStereoMatches).  `value` is whole-job frames/s with the batch resident in HBM;
 `e2e` is the same work through the host-buffer C-ABI calls with the H2D / D2H copies inside the
-timed region.  The reference arm times the CPU oracle (the restated reference path,
-oracle/oracle_cpu.cpp — the reference's C++ needs OpenCV/Eigen/Pangolin and cannot be built
-here) on all host cores, one frame pair per thread, on a bounded sample per step.
+timed region.  The reference arm (and the cpu_baseline leg of the own arm) times the reference's OWN ORBextractor.cc
+— compiled from /root/reference against an OpenCV API stand-in into oracle/_ref, see oracle/ref_shim — plus the restated
+Frame::ComputeStereoMatches (pinned bit-exact to the reference's Frame.cc) on all host cores, one frame pair per thread,
+on a bounded sample per step; where oracle/_ref is absent it falls back to the CPU oracle port (oracle/oracle_cpu.cpp).
 """
 import argparse
 import ctypes
@@ -24,9 +25,8 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "oracle")):
-    if p not in sys.path:
-        sys.path.insert(0, p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 import numpy as np
 
@@ -126,6 +126,9 @@ class ClockSampler:
 def cpu_reference():
     """(stereo_batch function, kind, description) of the CPU arm: the reference's own ORBextractor.cc where the checker
     built from /root/reference is present (oracle/_ref, travels with the snapshot), else the oracle port."""
+    oracle_dir = os.path.join(ROOT, "oracle")          # the ONLY place this file reaches into oracle/: the CPU arm
+    if oracle_dir not in sys.path:
+        sys.path.insert(0, oracle_dir)
     try:
         import ref
         if ref.available():
@@ -139,8 +142,8 @@ def cpu_reference():
 
 
 def make_inputs(pairs, seed):
-    import gen_synth
-    left, right = gen_synth.frame_batch(pairs, H, W, seed, stereo=True)
+    from refactored_orb_slam2_b200 import synthetic          # input generator only; nothing under oracle/ is touched by the own arm
+    left, right = synthetic.frame_batch(pairs, H, W, seed, stereo=True)
     return np.ascontiguousarray(np.concatenate([left, right]))        # [2*pairs, H, W]: left images then right images
 
 

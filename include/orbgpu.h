@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORBGPU_VERSION 140
+#define ORBGPU_VERSION 150
 
 enum {
   ORBGPU_OK = 0,
@@ -353,6 +353,20 @@ int orbgpu_remap_device(const uint8_t *d_src, int src_width, int src_height, siz
 int orbgpu_cvt_gray(const uint8_t *src, int channels, int code, int width, int height, uint8_t *dst, int batch, int device);
 int orbgpu_remap(const uint8_t *src, int src_width, int src_height, const float *map_x, const float *map_y, int width,
                  int height, uint8_t *dst, int batch, int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * MapPoint::ComputeDistinctiveDescriptors, batched
+ *
+ * src/MapPoint.cc:229-321: among the N descriptors observing a MapPoint take the one whose MEDIAN
+ * Hamming distance to all N (itself included, distance 0) is least — median = sorted[(size_t)(0.5*(N-1))],
+ * first minimum wins (:301-309).  One MapPoint is ~N^2/2 popcounts, far below the cost of a device call, so the
+ * entry point takes MANY MapPoints at once (LocalMapping::ProcessNewKeyFrame / CreateNewMapPoints update hundreds
+ * per keyframe): group g owns rows [offsets[g], offsets[g+1]) of `descriptors` ([rows][32], host), in the order the
+ * reference pushes them (iteration order of mObservations, bad keyframes skipped).
+ * best_index[g] = winning row relative to the group (-1 for an empty group), best_median[g] its median.
+ * ------------------------------------------------------------------------------------------------ */
+int orbgpu_distinctive_descriptors(const uint8_t *descriptors, const int32_t *offsets, int groups, int32_t *best_index,
+                                   int32_t *best_median, int device);
 
 /* Measured integer-pipe peak (register-resident POPC loop): returns POPC lane-ops per second. */
 int orbgpu_measure_popc_peak(int device, double *popc_per_second, double *lop3_per_second);

@@ -77,6 +77,7 @@ def lib():
         L.orb_oracle_voc_transform.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orb_oracle_cvt_gray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orb_oracle_remap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orb_oracle_distinctive.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orb_oracle_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
@@ -326,3 +327,13 @@ def remap(img, map_x, map_y):
     out = np.empty(mx.shape, np.uint8)
     lib().orb_oracle_remap(_p(a), a.shape[1], a.shape[0], _p(mx), _p(my), mx.shape[1], mx.shape[0], _p(out))
     return out
+
+
+def distinctive(descriptors, offsets):
+    """Restated MapPoint::ComputeDistinctiveDescriptors over groups of rows: (best index per group, its median)."""
+    d = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+    off = np.ascontiguousarray(offsets, np.int32)
+    g = len(off) - 1
+    idx, med = np.zeros(g, np.int32), np.zeros(g, np.int32)
+    lib().orb_oracle_distinctive(_p(d) if len(d) else None, _p(off), g, _p(idx), _p(med))
+    return idx, med

@@ -300,3 +300,25 @@ extern "C" void orb_oracle_remap(const uint8_t *src, int sw, int sh, const float
       dst[m] = (uint8_t)((v + (1 << 14)) >> 15);
     }
 }
+
+// ---- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:229-321), batched over groups of descriptor rows ----
+extern "C" void orb_oracle_distinctive(const uint8_t *descriptors, const int32_t *offsets, int groups, int32_t *bestIndex, int32_t *bestMedian) {
+  for (int g = 0; g < groups; g++) {
+    const int lo = offsets[g], N = offsets[g + 1] - lo;
+    if (N <= 0) { bestIndex[g] = -1; bestMedian[g] = 0; continue; }                       // :243-244, :257-258: nothing to do
+    std::vector<std::vector<int>> Distances(N, std::vector<int>(N, 0));                     // :287-296
+    for (int i = 0; i < N; i++)
+      for (int j = i + 1; j < N; j++) {
+        const int distij = descriptor_distance(descriptors + (size_t)(lo + i) * 32, descriptors + (size_t)(lo + j) * 32);
+        Distances[i][j] = distij; Distances[j][i] = distij;
+      }
+    int BestMedian = INT_MAX, BestIdx = 0;                                                   // :299-310
+    for (int i = 0; i < N; i++) {
+      std::vector<int> vDists(Distances[i].begin(), Distances[i].end());
+      std::sort(vDists.begin(), vDists.end());
+      const int median = vDists[(size_t)(0.5 * (N - 1))];
+      if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+    }
+    bestIndex[g] = BestIdx; bestMedian[g] = BestMedian;
+  }
+}

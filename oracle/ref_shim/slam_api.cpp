@@ -159,6 +159,22 @@ void slam_mappoint_set_descriptor(void *h, int mp, const uint8_t *d) {
   std::memcpy(m.ptr(0), d, 32);
   ((Scene *)h)->mps[mp]->mDescriptor = m;
 }
+// MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:229-321), the reference's own: returns the observation descriptors in
+// the order the reference visits them (its std::map<KeyFrame*, size_t>, bad keyframes skipped) and the descriptor it chose.
+int slam_mappoint_distinctive(void *h, int mp, uint8_t *rows, int cap, uint8_t *chosen) {
+  Scene *S = (Scene *)h;
+  MapPoint *p = S->mps[mp];
+  int n = 0;
+  for (auto &ob : p->mObservations) {
+    if (ob.first->isBad()) continue;
+    if (n < cap) std::memcpy(rows + (size_t)n * 32, ob.first->mDescriptors.ptr((int)ob.second), 32);
+    n++;
+  }
+  p->ComputeDistinctiveDescriptors();
+  cv::Mat d = p->GetDescriptor();
+  std::memcpy(chosen, d.ptr(0), 32);
+  return n;
+}
 void slam_mappoint_set_bad(void *h, int mp) { ((Scene *)h)->mps[mp]->SetBadFlag(); }
 void slam_mappoint_descriptor(void *h, int mp, uint8_t *out) { cv::Mat d = ((Scene *)h)->mps[mp]->GetDescriptor(); std::memcpy(out, d.ptr(0), 32); }
 void slam_frame_assoc(void *h, int f, int idx, int mp) { Scene *S = (Scene *)h; S->frames[f]->mvpMapPoints[idx] = mp < 0 ? nullptr : S->mps[mp]; }

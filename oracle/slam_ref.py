@@ -46,6 +46,7 @@ class SlamLib:
         L.slam_mappoint_update.argtypes = [_p, _i]
         L.slam_mappoint_set_bad.argtypes = [_p, _i]
         L.slam_mappoint_set_descriptor.argtypes = [_p, _i, _p]
+        L.slam_mappoint_distinctive.argtypes = [_p, _i, _p, _i, _p]
         L.slam_mappoint_descriptor.argtypes = [_p, _i, _p]
         L.slam_frame_assoc.argtypes = [_p, _i, _i, _i]
         L.slam_frame_outlier.argtypes = [_p, _i, _i, _i]

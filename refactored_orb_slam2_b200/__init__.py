@@ -4,11 +4,11 @@ ORBextractor / ORBmatcher / Frame::ComputeStereoMatches interfaces.  No CPU fall
 from ._lib import KP_DTYPE, TOP2_DTYPE, OrbGpuError, lib  # noqa: F401
 from .extractor import ORBextractor  # noqa: F401
 from .features import FrameFeatures, grid_geometry, make_policy  # noqa: F401
-from .matcher import DescriptorBank, ORBmatcher, merge_top2_device  # noqa: F401
+from .matcher import DescriptorBank, ORBmatcher, distinctive_descriptors, merge_top2_device  # noqa: F401
 from .stereo import ComputeStereoMatches, Frame  # noqa: F401
 from .pipeline import StereoBatchPipeline  # noqa: F401
 from .vocabulary import Vocabulary  # noqa: F401
 from . import staging  # noqa: F401
 
-__all__ = ["ORBextractor", "FrameFeatures", "grid_geometry", "make_policy", "Vocabulary", "ORBmatcher", "DescriptorBank", "ComputeStereoMatches", "Frame", "StereoBatchPipeline", "merge_top2_device",
+__all__ = ["ORBextractor", "FrameFeatures", "grid_geometry", "make_policy", "Vocabulary", "distinctive_descriptors", "ORBmatcher", "DescriptorBank", "ComputeStereoMatches", "Frame", "StereoBatchPipeline", "merge_top2_device",
            "KP_DTYPE", "TOP2_DTYPE", "OrbGpuError", "lib"]

@@ -104,6 +104,7 @@ SYMBOLS = {
     "orbgpu_remap_device": (_i, [_vp, _i, _i, _sz, _sz, _vp, _vp, _i, _i, _vp, _sz, _sz, _i, _vp]),
     "orbgpu_cvt_gray": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i]),
     "orbgpu_remap": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i]),
+    "orbgpu_distinctive_descriptors": (_i, [_vp, _vp, _i, _vp, _vp, _i]),
     "orbgpu_measure_popc_peak": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "orbgpu_measure_pipe": (_i, [_i, _i, C.POINTER(C.c_double)]),
     "orbgpu_launch_count": (_i64, [_i]),

@@ -765,3 +765,68 @@ int orbgpu_vocabulary_transform_features(orbgpu_vocabulary *v, orbgpu_features *
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:229-321), one warp per MapPoint.  For row i the lanes take the
+// columns j in strides of 32; the median (k-th smallest of the N distances, k = floor((N - 1) / 2), the 0 to itself
+// included) is found by bisection on the threshold t over [0, 256]: smallest t with |{j : d(i, j) <= t}| >= k + 1.
+namespace orbgpu {
+namespace {
+__global__ void __launch_bounds__(128) k_distinctive(const uint4 *__restrict__ desc, const int *__restrict__ offsets, int groups, int *__restrict__ bestIndex,
+                                                      int *__restrict__ bestMedian) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (g >= groups) return;
+  const int lo0 = offsets[g], n = offsets[g + 1] - lo0;
+  int best = -1, bestMed = 0x7fffffff;
+  const int k = (n - 1) >> 1;                              // (size_t)(0.5 * (N - 1))
+  for (int i = 0; i < n; i++) {
+    const uint4 a0 = desc[2 * (size_t)(lo0 + i)], a1 = desc[2 * (size_t)(lo0 + i) + 1];
+    int lo = 0, hi = 256;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      int cnt = 0;
+      for (int j = lane; j < n; j += 32) cnt += hamming256(a0, a1, desc + 2 * (size_t)(lo0 + j)) <= mid;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (cnt >= k + 1) hi = mid; else lo = mid + 1;
+    }
+    if (lo < bestMed) { bestMed = lo; best = i; }          // strict '<': the first minimum wins (MapPoint.cc:306)
+  }
+  if (lane == 0) { bestIndex[g] = best; bestMedian[g] = n > 0 ? bestMed : 0; }
+}
+}  // namespace
+}  // namespace orbgpu
+
+extern "C" int orbgpu_distinctive_descriptors(const uint8_t *descriptors, const int32_t *offsets, int groups, int32_t *best_index, int32_t *best_median,
+                                              int device) {
+  if (groups < 0 || (groups > 0 && (!offsets || !best_index || !best_median))) { set_error("bad arguments"); return ORBGPU_E_INVALID; }
+  if (groups == 0) return ORBGPU_OK;
+  for (int g = 0; g < groups; g++)
+    if (offsets[g] > offsets[g + 1] || offsets[g] < 0) { set_error("offsets must be non-decreasing"); return ORBGPU_E_INVALID; }
+  const int rows = offsets[groups];
+  if (rows > 0 && !descriptors) { set_error("null descriptors"); return ORBGPU_E_INVALID; }
+  if (orbgpu_device_count() < 1) { set_error("no CUDA device available (this library has no CPU path)"); return ORBGPU_E_CUDA; }
+  DevGuard guard(device);
+  if (!guard.ok) { set_error("cannot select device %d", device); return ORBGPU_E_CUDA; }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  Workspace &W = t_ws;
+  const size_t oD = 0, oO = align16((size_t)std::max(rows, 1) * 32), total = align16(oO + (size_t)(groups + 1) * sizeof(int));
+  cudaError_t e = ensure(W, dev, total, (size_t)groups, 0);
+  if (e != cudaSuccess) { set_error("workspace allocation failed: %s", cudaGetErrorString(e)); return ORBGPU_E_CUDA; }
+  if (rows) std::memcpy(W.hStage + oD, descriptors, (size_t)rows * 32);
+  std::memcpy(W.hStage + oO, offsets, (size_t)(groups + 1) * sizeof(int));
+  cudaStream_t s = W.stream;
+  ORBGPU_CUDA_CHECK(cudaMemcpyAsync(W.dStage, W.hStage, total, cudaMemcpyHostToDevice, s));
+  int *dOut = reinterpret_cast<int *>(W.dRes[0]);          // [index groups | median groups]
+  k_distinctive<<<(groups + 3) / 4, 128, 0, s>>>(reinterpret_cast<const uint4 *>(W.dStage + oD), reinterpret_cast<const int *>(W.dStage + oO), groups, dOut,
+                                                 dOut + groups);
+  count_launch();
+  ORBGPU_CUDA_CHECK(cudaGetLastError());
+  int *hOut = reinterpret_cast<int *>(W.hRes);
+  ORBGPU_CUDA_CHECK(cudaMemcpyAsync(hOut, dOut, (size_t)2 * groups * sizeof(int), cudaMemcpyDeviceToHost, s));
+  ORBGPU_CUDA_CHECK(cudaStreamSynchronize(s));
+  std::memcpy(best_index, hOut, (size_t)groups * sizeof(int));
+  std::memcpy(best_median, hOut + groups, (size_t)groups * sizeof(int));
+  return ORBGPU_OK;
+}

@@ -66,6 +66,17 @@ def merge_top2_device(d_parts, parts, nq, d_result, nnratio=0.0, th_low=0, d_mat
                                          C.c_void_p(int(d_match)) if d_match else None, device, C.c_void_p(stream or 0)))
 
 
+def distinctive_descriptors(descriptors, offsets, device=-1):
+    """MapPoint::ComputeDistinctiveDescriptors (Source/Libraries/ORB_SLAM2/src/MapPoint.cc:229-321) for many MapPoints at
+    once: group g = rows offsets[g]:offsets[g+1] (observation order); returns (best row per group, relative; its median)."""
+    d = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32)
+    off = np.ascontiguousarray(offsets, np.int32)
+    g = len(off) - 1
+    idx, med = np.zeros(g, np.int32), np.zeros(g, np.int32)
+    check(lib().orbgpu_distinctive_descriptors(ptr(d) if len(d) else None, ptr(off), g, ptr(idx), ptr(med), device))
+    return idx, med
+
+
 class ORBmatcher:
     TH_HIGH = 100        # ORBmatcher.cc:38-40
     TH_LOW = 50

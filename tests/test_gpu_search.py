@@ -264,3 +264,21 @@ def test_concurrent_searches_from_three_threads_share_one_feature_set(pkg):
     for t in th:
         t.join()
     assert not bad
+
+
+def test_distinctive_descriptors_vs_oracle(pkg):
+    """Row f4: batched MapPoint::ComputeDistinctiveDescriptors — groups of 1..70 observations, ties, empty groups."""
+    rng = np.random.default_rng(4)
+    sizes = np.concatenate([rng.integers(1, 12, 3000), rng.integers(12, 70, 200), [0, 1, 2, 2, 33, 64, 65]])
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    base = rng.integers(0, 256, (len(sizes), 32), dtype=np.uint8)
+    rows = np.repeat(base, sizes, axis=0)
+    flip = rng.integers(0, 256, rows.shape, dtype=np.uint8) & rng.integers(0, 256, rows.shape, dtype=np.uint8) & rng.integers(0, 256, rows.shape, dtype=np.uint8)
+    rows ^= flip
+    rows[offsets[-3]:offsets[-3] + 10] = rows[offsets[-3]]          # identical rows: the first wins
+    gi, gm = pkg.distinctive_descriptors(rows, offsets)
+    oi, om = oracle.distinctive(rows, offsets)
+    assert np.array_equal(gi, oi) and np.array_equal(gm, om)
+    assert gi[len(sizes) - 7] == -1
+    i0, m0 = pkg.distinctive_descriptors(np.zeros((0, 32), np.uint8), np.zeros(1, np.int32))
+    assert len(i0) == 0

@@ -81,3 +81,26 @@ def test_reference_stereo_frame_constructor_grid_equals_oracle_grid():
     o = oracle.OracleFeatures(out["keys"], out["desc"], out["u_right"], geo)
     start, items = o.grid()
     assert np.array_equal(start, out["cell_start"]) and np.array_equal(items, out["cell_items"])
+
+
+def test_reference_compute_distinctive_descriptors_equals_oracle():
+    """Row f4: the reference's own MapPoint::ComputeDistinctiveDescriptors on MapPoints observed from 12 keyframes; the oracle's
+    batched restatement, fed the observation descriptors in the reference's own visiting order, must choose the same one."""
+    lib = slam_ref.SlamLib("ref")
+    W = slam_ref.World(17, npoints=400, clutter=60, flips=70)
+    S = slam_ref.Scene(lib, W)
+    views = [W.observe(slam_ref._pose(0.002 * i, -0.01 * i, 0.0, [-0.12 * i, 0.0, -0.1 * i])) for i in range(12)]
+    kfs = [S.add_keyframe(S.add_frame(V)) for V in views]
+    obs = {p: o for p, o in slam_ref.observations_from_views(views).items() if len(o) >= 3}
+    S.add_mappoints(obs)
+    rows, offsets, chosen = [], [0], []
+    for mp in range(S.n_mps):
+        buf, out = np.zeros((16, 32), np.uint8), np.zeros(32, np.uint8)
+        n = lib.L.slam_mappoint_distinctive(S.h, mp, slam_ref._ptr(buf), 16, slam_ref._ptr(out))
+        rows.append(buf[:n]); offsets.append(offsets[-1] + n); chosen.append(out)
+    rows = np.concatenate(rows)
+    idx, med = oracle.distinctive(rows, offsets)
+    assert S.n_mps > 200 and max(np.diff(offsets)) >= 10
+    for g in range(S.n_mps):
+        assert np.array_equal(rows[offsets[g] + idx[g]], chosen[g]), g
+    S.close()

@@ -349,7 +349,16 @@ def run_own(args, rank, local_rank, world):
         cur = torch.cuda.Stream()          # an explicit side stream: a NULL stream argument means "the bank's own stream"
         torch.cuda.set_stream(cur)
 
+        use_peer = world > 1 and args.hamming_exchange == "peer"
+        if use_peer:
+            from refactored_orb_slam2_b200.distributed import PeerExchange
+            xchg = PeerExchange(rank, world, HAMMING_NQ, local_rank)      # IPC handles all-gathered once; no collective afterwards
+
         def step_hamming():
+            if use_peer:      # scan -> records stored into every peer's window over NVLink -> wait on arrival flags + merge
+                pkg._lib.check(lib.orbgpu_hamming_top2_sharded_device(bank._h, xchg._h, vp(d_q.data_ptr()), HAMMING_NQ, vp(merged.data_ptr()), 0.7, 50,
+                                                                      vp(match.data_ptr()), vp(cur.cuda_stream)))
+                return
             bank.top2_device(d_q.data_ptr(), HAMMING_NQ, local.data_ptr(), stream=cur.cuda_stream)
             if world > 1:
                 dist.all_gather_into_tensor(gathered, local)
@@ -370,6 +379,8 @@ def run_own(args, rank, local_rank, world):
         h1.record(cur)
         barrier()
         hms = max_over_ranks(h0.elapsed_time(h1)) / hsteps
+        if use_peer:
+            xchg.check()                   # a peer whose records never arrived would have been recorded on the device
         gpairs = HAMMING_NQ * HAMMING_BANK / (hms * 1e-3) / 1e9
         popc, lop3 = ctypes.c_double(), ctypes.c_double()
         pkg._lib.check(lib.orbgpu_measure_popc_peak(local_rank, ctypes.byref(popc), ctypes.byref(lop3)))
@@ -377,6 +388,8 @@ def run_own(args, rank, local_rank, world):
         peak_gpairs = world * popc.value / 8 / 1e9
         hamming = {"metric": "Hamming match Gpairs/s (2000 queries x 1M-row bank, top-2 + ratio 0.7 / TH_LOW 50)",
                    "value": gpairs, "unit": "Gpairs/s", "ms_per_step": hms, "scaling": "strong", "shards": world,
+                   "exchange": ("none (one shard)" if world == 1 else "peer-memory stores over NVLink + arrival flags, fused with the shard merge; no collective call"
+                                if use_peer else "one NCCL all-gather of 16 B per query per rank + merge kernel"),
                    "roofline": {"bound": "integer-pipe (POPC)", "achieved": gpairs, "peak": peak_gpairs, "unit": "Gpairs/s",
                                 "frac": gpairs / peak_gpairs,
                                 "note": "peak = measured POPC issue rate / 8 POPC per pair (algorithmic); the kernel's carry-save "
@@ -461,6 +474,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=160, help="stereo pairs per step per GPU (320 images = 149 MB > L2)")
     ap.add_argument("--ref-pairs", type=int, default=0)
     ap.add_argument("--no-hamming", action="store_true")
+    ap.add_argument("--hamming-exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the per-shard top-2 records travel: the library's peer-memory kernels (default) or one NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORBGPU_VERSION 150
+#define ORBGPU_VERSION 160
 
 enum {
   ORBGPU_OK = 0,
@@ -180,6 +180,31 @@ int orbgpu_hamming_top2_dense_device(orbgpu_bank *bank, const uint8_t *d_queries
  * of src/ORBmatcher.cc:224-226 (d1 <= th_low && d1 < nnratio*d2): d_match[i] = idx1 or -1. */
 int orbgpu_top2_merge_device(const void *d_parts, int parts, int nq, void *d_result, float nnratio,
                              int th_low, int64_t *d_match, int device, void *stream);
+
+/* ---- row-sharded bank across the GPUs of one node: scan + exchange + merge without a collective library ----
+ * One process per GPU.  Every rank owns a window in its HBM ([2 epochs][world][max_queries] 16-byte records + arrival
+ * flags) that its peers map through CUDA IPC.  orbgpu_hamming_top2_sharded_device then runs, on `stream`:
+ *   1. the bank scan of this rank's shard (as orbgpu_hamming_top2_dense_device);
+ *   2. ONE kernel that folds the shard's chunk partials per query and stores the 16-byte record straight into EVERY
+ *      peer's window over NVLink (peer stores), the last CTA publishing this rank's arrival flag in every window;
+ *   3. ONE kernel that waits for the `world` arrival flags of the current epoch in the LOCAL window and folds the
+ *      records in rank order (= ascending bank index), applying the acceptance test of src/ORBmatcher.cc:224-226.
+ * The exchange therefore starts the moment a rank's scan ends and costs no host round trip and no NCCL launch; the
+ * result is identical on every rank and identical to one sequential scan of the whole bank.  Windows alternate between
+ * two epochs, so a fast rank can run one step ahead of a slow one, never two.  A peer that does not arrive within
+ * ~2 s makes the call's NEXT invocation (or orbgpu_exchange_check) fail with ORBGPU_E_CUDA instead of hanging. */
+typedef struct orbgpu_exchange orbgpu_exchange;
+#define ORBGPU_IPC_HANDLE_BYTES 64
+/* Allocates this rank's window and writes its IPC handle (to be all-gathered by the caller's process group). */
+int orbgpu_exchange_create(int rank, int world, int max_queries, int device, orbgpu_exchange **out,
+                           uint8_t *handle /* [ORBGPU_IPC_HANDLE_BYTES] */);
+/* Maps the peers' windows: handles = [world][ORBGPU_IPC_HANDLE_BYTES] in rank order (own entry ignored). */
+int orbgpu_exchange_connect(orbgpu_exchange *x, const uint8_t *handles);
+int orbgpu_exchange_check(orbgpu_exchange *x);     /* synchronises nothing; reports a recorded arrival timeout */
+void orbgpu_exchange_destroy(orbgpu_exchange *x);
+/* d_result: nq merged { d1, d2, idx } records (may be NULL); d_match: nq accepted global indices or -1 (may be NULL). */
+int orbgpu_hamming_top2_sharded_device(orbgpu_bank *bank, orbgpu_exchange *x, const uint8_t *d_queries, int nq,
+                                       void *d_result, float nnratio, int th_low, int64_t *d_match, void *stream);
 
 /* Candidate-list form used by the projection / BoW searches: query i scans train rows
  * cand[offsets[i] .. offsets[i+1]) in list order.  Host pointers; idx1 is a train row or -1. */

@@ -87,6 +87,11 @@ SYMBOLS = {
     "orbgpu_hamming_top2_dense": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "orbgpu_hamming_top2_dense_device": (_i, [_vp, _vp, _i, _vp, _vp]),
     "orbgpu_top2_merge_device": (_i, [_vp, _i, _i, _vp, _f, _i, _vp, _i, _vp]),
+    "orbgpu_exchange_create": (_i, [_i, _i, _i, _i, C.POINTER(_vp), _vp]),
+    "orbgpu_exchange_connect": (_i, [_vp, _vp]),
+    "orbgpu_exchange_check": (_i, [_vp]),
+    "orbgpu_exchange_destroy": (None, [_vp]),
+    "orbgpu_hamming_top2_sharded_device": (_i, [_vp, _vp, _vp, _i, _vp, _f, _i, _vp, _vp]),
     "orbgpu_hamming_top2_csr": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i]),
     "orbgpu_features_create": (_i, [C.POINTER(FeaturesDesc), C.POINTER(_vp)]),
     "orbgpu_features_from_extractor": (_i, [_vp, _i, _i, C.POINTER(FeaturesDesc), C.POINTER(_vp)]),

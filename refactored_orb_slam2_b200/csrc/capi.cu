@@ -979,6 +979,109 @@ int orbgpu_hamming_top2_dense(orbgpu_bank *b, const uint8_t *queries, int nq, in
   return ORBGPU_OK;
 }
 
+struct orbgpu_exchange {
+  int rank = 0, world = 1, maxQueries = 0, device = 0;
+  char *window = nullptr;                 // this rank's window (exported through CUDA IPC)
+  std::vector<char *> peer;               // every rank's window as mapped here (peer[rank] == window)
+  char **dPeers = nullptr;                // device copy of `peer`
+  unsigned *dDone = nullptr, *dError = nullptr;
+  unsigned epoch = 0;
+  bool connected = false;
+};
+
+int orbgpu_exchange_create(int rank, int world, int max_queries, int device, orbgpu_exchange **out, uint8_t *handle) {
+  if (!out || !handle || world < 1 || world > 32 || rank < 0 || rank >= world || max_queries < 1) { set_error("bad exchange arguments"); return ORBGPU_E_INVALID; }
+  *out = nullptr;
+  static_assert(sizeof(cudaIpcMemHandle_t) == ORBGPU_IPC_HANDLE_BYTES, "IPC handle size");
+  if (orbgpu_device_count() < 1) { set_error("no CUDA device available (this library has no CPU path)"); return ORBGPU_E_CUDA; }
+  DeviceGuard guard(device);
+  orbgpu_exchange *x = new orbgpu_exchange;
+  x->rank = rank; x->world = world; x->maxQueries = max_queries;
+  cudaGetDevice(&x->device);
+  const size_t bytes = exchange_window_bytes(world, max_queries);
+  cudaError_t e = cudaMalloc(&x->window, bytes);
+  if (e == cudaSuccess) e = cudaMemset(x->window, 0, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&x->dPeers, sizeof(char *) * world);
+  if (e == cudaSuccess) e = cudaMalloc(&x->dDone, 2 * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemset(x->dDone, 0, 2 * sizeof(unsigned));
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, x->window);
+  if (e != cudaSuccess) { set_error("exchange_create: %s", cudaGetErrorString(e)); orbgpu_exchange_destroy(x); return ORBGPU_E_CUDA; }
+  x->dError = x->dDone + 1;
+  std::memcpy(handle, &h, sizeof(h));
+  x->peer.assign(world, nullptr);
+  x->peer[rank] = x->window;
+  if (world == 1) {
+    if (cudaMemcpy(x->dPeers, x->peer.data(), sizeof(char *), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("exchange_create: copy failed"); orbgpu_exchange_destroy(x); return ORBGPU_E_CUDA; }
+    x->connected = true;
+  }
+  *out = x;
+  return ORBGPU_OK;
+}
+
+int orbgpu_exchange_connect(orbgpu_exchange *x, const uint8_t *handles) {
+  if (!x || !handles) { set_error("null argument"); return ORBGPU_E_INVALID; }
+  DeviceGuard guard(x->device);
+  for (int r = 0; r < x->world; r++) {
+    if (r == x->rank || x->peer[r]) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + (size_t)r * ORBGPU_IPC_HANDLE_BYTES, sizeof(h));
+    void *p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { set_error("cannot map the window of rank %d: %s", r, cudaGetErrorString(e)); return ORBGPU_E_CUDA; }
+    x->peer[r] = (char *)p;
+  }
+  ORBGPU_CUDA_CHECK(cudaMemcpy(x->dPeers, x->peer.data(), sizeof(char *) * x->world, cudaMemcpyHostToDevice));
+  x->connected = true;
+  return ORBGPU_OK;
+}
+
+int orbgpu_exchange_check(orbgpu_exchange *x) {
+  if (!x) { set_error("null exchange"); return ORBGPU_E_INVALID; }
+  DeviceGuard guard(x->device);
+  unsigned err = 0;
+  ORBGPU_CUDA_CHECK(cudaMemcpy(&err, x->dError, sizeof(err), cudaMemcpyDeviceToHost));
+  if (err) { set_error("rank %d: the records of rank %u did not arrive within 2 s", x->rank, err - 1); return ORBGPU_E_CUDA; }
+  return ORBGPU_OK;
+}
+
+void orbgpu_exchange_destroy(orbgpu_exchange *x) {
+  if (!x) return;
+  DeviceGuard guard(x->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < (int)x->peer.size(); r++)
+    if (r != x->rank && x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);
+  cudaFree(x->window); cudaFree(x->dPeers); cudaFree(x->dDone);
+  delete x;
+}
+
+int orbgpu_hamming_top2_sharded_device(orbgpu_bank *b, orbgpu_exchange *x, const uint8_t *d_queries, int nq, void *d_result, float nnratio,
+                                       int th_low, int64_t *d_match, void *stream) {
+  if (!b || !x || nq < 0 || (nq > 0 && !d_queries)) { set_error("bad arguments"); return ORBGPU_E_INVALID; }
+  if (!x->connected) { set_error("exchange not connected"); return ORBGPU_E_INVALID; }
+  if (nq > x->maxQueries) { set_error("%d queries exceed the exchange window (%d)", nq, x->maxQueries); return ORBGPU_E_CAPACITY; }
+  if (b->device != x->device) { set_error("bank and exchange live on different devices"); return ORBGPU_E_INVALID; }
+  if (nq == 0) return ORBGPU_OK;
+  if (((uintptr_t)d_queries & 15) != 0 || ((uintptr_t)d_result & 15) != 0) { set_error("queries / results must be 16-byte aligned"); return ORBGPU_E_INVALID; }
+  DeviceGuard guard(b->device);
+  cudaStream_t s = stream ? (cudaStream_t)stream : b->stream;
+  const int chunks = hamming_dense_chunks(b->rows, nq, b->smCount);
+  const size_t need = (size_t)chunks * nq;
+  if (need > b->partialCap) {
+    ORBGPU_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (b->partial) cudaFree(b->partial);
+    b->partialCap = need;
+    ORBGPU_CUDA_CHECK(cudaMalloc(&b->partial, need * sizeof(Top2Rec)));
+  }
+  ExchangeView V;
+  V.rank = x->rank; V.world = x->world; V.maxQueries = x->maxQueries; V.peers = x->dPeers; V.local = x->window; V.done = x->dDone; V.error = x->dError;
+  const unsigned epoch = ++x->epoch;
+  ORBGPU_CUDA_CHECK(launch_hamming_scan_only(b->d, b->rows, b->indexBase, d_queries, nq, b->partial, chunks, s));
+  ORBGPU_CUDA_CHECK(launch_top2_push(b->partial, b->rows > 0 ? chunks : 0, nq, V, epoch, s));
+  ORBGPU_CUDA_CHECK(launch_top2_wait_merge(nq, V, epoch, (Top2Rec *)d_result, nnratio, th_low, (long long *)d_match, s));
+  return ORBGPU_OK;
+}
+
 int orbgpu_top2_merge_device(const void *d_parts, int parts, int nq, void *d_result, float nnratio, int th_low,
                              int64_t *d_match, int device, void *stream) {
   if (parts < 0 || nq < 0 || (nq > 0 && parts > 0 && !d_parts)) { set_error("bad arguments"); return ORBGPU_E_INVALID; }

@@ -183,6 +183,95 @@ k_top2_merge(const Top2Rec *__restrict__ parts, int nparts, int nq, Top2Rec *__r
   }
 }
 
+__device__ __forceinline__ Top2Rec *window_records(char *base, const ExchangeView &x, unsigned epoch, int rank) {
+  return reinterpret_cast<Top2Rec *>(base) + ((size_t)(epoch & 1u) * x.world + rank) * x.maxQueries;
+}
+__device__ __forceinline__ unsigned *window_flags(char *base, const ExchangeView &x, unsigned epoch) {
+  return reinterpret_cast<unsigned *>(base + (size_t)2 * x.world * x.maxQueries * sizeof(Top2Rec) + 128) + (size_t)(epoch & 1u) * x.world;
+}
+
+// Folds this shard's chunk partials per query (as k_top2_merge) and stores the record into EVERY rank's window — peer
+// stores over NVLink, 16 bytes per query and peer; the last CTA to finish publishes this rank's arrival flag everywhere.
+__global__ void __launch_bounds__(256)
+k_top2_push(const Top2Rec *__restrict__ parts, int nparts, int nq, const ExchangeView x, unsigned epoch) {
+  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (qi < nq) {
+    int d1 = 256, d2 = 256;
+    long long idx = -1;
+    for (int p = lane; p < nparts; p += 32) {
+      const Top2Rec r = parts[(size_t)p * nq + qi];
+      fold_top2(d1, d2, idx, r.d1, r.d2, r.idx);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int e1 = __shfl_xor_sync(0xffffffffu, d1, o);
+      const int e2 = __shfl_xor_sync(0xffffffffu, d2, o);
+      const long long eidx = __shfl_xor_sync(0xffffffffu, idx, o);
+      fold_top2(d1, d2, idx, e1, e2, eidx);
+    }
+    // lanes 0 .. world-1 each serve one destination rank: one 16-byte store per peer
+    if (lane < x.world) {
+      int4 v;
+      v.x = d1; v.y = d2; v.z = (int)(unsigned)(idx & 0xffffffffll); v.w = (int)(idx >> 32);
+      *reinterpret_cast<int4 *>(window_records(x.peers[lane], x, epoch, x.rank) + qi) = v;
+    }
+  }
+  __threadfence_system();                                  // this thread's peer stores are visible system-wide ...
+  __syncthreads();                                         // ... for every thread of the CTA
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(x.done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last && threadIdx.x < x.world) {
+    __threadfence_system();
+    volatile unsigned *flag = window_flags(x.peers[threadIdx.x], x, epoch) + x.rank;
+    *flag = epoch;                                         // arrival of rank x.rank in rank threadIdx.x's window
+    if (threadIdx.x == 0) *x.done = 0u;                    // re-arm for the next step (stream order separates the steps)
+  }
+}
+
+// Waits until every rank's records of `epoch` have arrived in the LOCAL window, then folds them in rank order.
+__global__ void __launch_bounds__(256)
+k_top2_wait_merge(int nq, const ExchangeView x, unsigned epoch, Top2Rec *__restrict__ result, float nnratio, int thLow,
+                  long long *__restrict__ match) {
+  if (threadIdx.x < x.world) {
+    volatile unsigned *flag = window_flags(x.local, x, epoch) + threadIdx.x;
+    unsigned long long t0 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*flag != epoch) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 2000000000ull) { atomicExch(x.error, 1u + (unsigned)threadIdx.x); break; }   // a peer never arrived: report, do not hang
+      __nanosleep(200);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (qi >= nq) return;
+  int d1 = 256, d2 = 256;
+  long long idx = -1;
+  for (int r = lane; r < x.world; r += 32) {
+    const int4 v = __ldcg(reinterpret_cast<const int4 *>(window_records(x.local, x, epoch, r) + qi));   // L2: where the peer stores land
+    fold_top2(d1, d2, idx, v.x, v.y, ((long long)v.w << 32) | (unsigned)v.z);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int e1 = __shfl_xor_sync(0xffffffffu, d1, o);
+    const int e2 = __shfl_xor_sync(0xffffffffu, d2, o);
+    const long long eidx = __shfl_xor_sync(0xffffffffu, idx, o);
+    fold_top2(d1, d2, idx, e1, e2, eidx);
+  }
+  if (lane == 0) {
+    if (result) { Top2Rec o; o.d1 = d1; o.d2 = d2; o.idx = idx; result[qi] = o; }
+    if (match) {
+      const bool ok = d1 <= thLow && (float)d1 < __fmul_rn(nnratio, (float)d2);   // ORBmatcher.cc:224-226
+      match[qi] = ok ? idx : -1ll;
+    }
+  }
+}
+
 // Candidate-list scan: one warp per query, lanes stride the list; merge keeps list order semantics.
 __global__ void k_hamming_csr(const uint8_t *__restrict__ queries, int nq, const uint8_t *__restrict__ train,
                               const int *__restrict__ offsets, const int *__restrict__ cand, int *__restrict__ idx1,
@@ -286,8 +375,8 @@ static void launch_dense_q(int variant, dim3 grid, cudaStream_t s, const uint8_t
   }
 }
 
-cudaError_t launch_hamming_dense(const uint8_t *bank, int rows, long long indexBase, const uint8_t *q,
-                                 int nq, Top2Rec *partial, int chunks, Top2Rec *result, cudaStream_t s) {
+cudaError_t launch_hamming_scan_only(const uint8_t *bank, int rows, long long indexBase, const uint8_t *q, int nq, Top2Rec *partial,
+                                     int chunks, cudaStream_t s) {
   if (nq <= 0) return cudaSuccess;
   static const int variant = [] { const char *e = getenv("ORBGPU_HAMMING_VARIANT"); return e ? atoi(e) : 2; }();
   if (rows > 0) {
@@ -304,7 +393,34 @@ cudaError_t launch_hamming_dense(const uint8_t *bank, int rows, long long indexB
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
+  return cudaSuccess;
+}
+
+cudaError_t launch_hamming_dense(const uint8_t *bank, int rows, long long indexBase, const uint8_t *q,
+                                 int nq, Top2Rec *partial, int chunks, Top2Rec *result, cudaStream_t s) {
+  if (nq <= 0) return cudaSuccess;
+  cudaError_t e = launch_hamming_scan_only(bank, rows, indexBase, q, nq, partial, chunks, s);
+  if (e != cudaSuccess) return e;
   return launch_top2_merge(partial, rows > 0 ? chunks : 0, nq, result, 0.f, 0, nullptr, s);
+}
+
+// ---- sharded bank: window layout, push and wait + merge ------------------------------------------------------------
+// window = [2 epochs][world][maxQueries] Top2Rec, then [2][world] arrival flags (u32, padded to 128 B)
+size_t exchange_window_bytes(int world, int maxQueries) {
+  return (size_t)2 * world * maxQueries * sizeof(Top2Rec) + 128 + (size_t)2 * world * sizeof(unsigned) + 128;
+}
+cudaError_t launch_top2_push(const Top2Rec *partial, int nparts, int nq, const ExchangeView &x, unsigned epoch, cudaStream_t s) {
+  if (nq <= 0) return cudaSuccess;
+  k_top2_push<<<(nq + 7) / 8, 256, 0, s>>>(partial, nparts, nq, x, epoch);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_top2_wait_merge(int nq, const ExchangeView &x, unsigned epoch, Top2Rec *result, float nnratio, int thLow,
+                                   long long *match, cudaStream_t s) {
+  if (nq <= 0) return cudaSuccess;
+  k_top2_wait_merge<<<(nq + 7) / 8, 256, 0, s>>>(nq, x, epoch, result, nnratio, thLow, match);
+  count_launch();
+  return cudaGetLastError();
 }
 
 cudaError_t launch_top2_merge(const Top2Rec *parts, int nparts, int nq, Top2Rec *result, float nnratio,

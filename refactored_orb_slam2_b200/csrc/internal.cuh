@@ -164,6 +164,20 @@ cudaError_t launch_hamming_dense(const uint8_t *bank, int rows, long long indexB
 int hamming_dense_chunks(int rows, int nq, int smCount);
 cudaError_t launch_top2_merge(const Top2Rec *parts, int nparts, int nq, Top2Rec *result, float nnratio,
                               int thLow, long long *match, cudaStream_t s);
+// sharded bank: push the shard's merged records into every peer's window / wait for all shards and fold them
+struct ExchangeView {
+  int rank, world, maxQueries;
+  char *const *peers;        // device array [world]: base of every rank's window as mapped in THIS process
+  char *local;               // base of this rank's own window
+  unsigned *done;            // last-CTA counter (local)
+  unsigned *error;           // arrival timeout flag (local)
+};
+size_t exchange_window_bytes(int world, int maxQueries);
+cudaError_t launch_top2_push(const Top2Rec *partial, int nparts, int nq, const ExchangeView &x, unsigned epoch, cudaStream_t s);
+cudaError_t launch_top2_wait_merge(int nq, const ExchangeView &x, unsigned epoch, Top2Rec *result, float nnratio, int thLow,
+                                   long long *match, cudaStream_t s);
+cudaError_t launch_hamming_scan_only(const uint8_t *bank, int rows, long long indexBase, const uint8_t *q, int nq, Top2Rec *partial,
+                                     int chunks, cudaStream_t s);
 cudaError_t launch_hamming_csr(const uint8_t *q, int nq, const uint8_t *train, const int *offsets,
                                const int *cand, int *idx1, int *d1, int *d2, cudaStream_t s);
 cudaError_t launch_pair_distance(const uint8_t *a, const uint8_t *b, int n, int *dist, cudaStream_t s);

@@ -24,7 +24,7 @@ def test_header_and_library_agree(built):
     for n in names:
         assert hasattr(lib, n), "liborbgpu.so does not export %s" % n
     assert sorted(L.SYMBOLS) == names, "python binding table and header drifted apart"
-    assert L.lib().orbgpu_version() == 150
+    assert L.lib().orbgpu_version() == 160
 
 
 def test_keypoint_record_is_cv_keypoint_layout(built):

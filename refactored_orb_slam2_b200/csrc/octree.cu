@@ -27,7 +27,10 @@ namespace orbgpu {
 
 namespace {
 
-constexpr int kThreads = 512;
+#ifndef ORBGPU_OCTREE_THREADS
+#define ORBGPU_OCTREE_THREADS 256      // measured on B200 (KITTI batch): 128 -> 0.47 ms, 192 -> 0.41, 256 -> 0.34, 512 -> 0.40, 1024 -> 0.57
+#endif
+constexpr int kThreads = ORBGPU_OCTREE_THREADS;
 constexpr int kWarps = kThreads / 32;
 
 struct Smem {

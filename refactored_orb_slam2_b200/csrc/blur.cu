@@ -23,9 +23,15 @@ namespace orbgpu {
 
 namespace {
 
-constexpr int kTW = 128, kTH = 64;
+#ifndef ORBGPU_BLUR_TH
+#define ORBGPU_BLUR_TH 64
+#endif
+#ifndef ORBGPU_BLUR_WARPS
+#define ORBGPU_BLUR_WARPS 4
+#endif
+constexpr int kTW = 128, kTH = ORBGPU_BLUR_TH;
 constexpr int kBoxW = kTW + 16, kBoxH = kTH + 6;
-constexpr int kWarpsPerCta = 4;
+constexpr int kWarpsPerCta = ORBGPU_BLUR_WARPS;
 constexpr int kSlotBytes = (kBoxW * kBoxH + 127) & ~127;
 
 // bytes O, O+1 of the 12-byte window (w0, w1, w2) zero-extended into packed 16x2

@@ -302,6 +302,7 @@ int configure(orbgpu_extractor *e, int w, int h) {
     octMax[d] = std::max(octMax[d], octSmem);
     fastMax[d] = std::max(fastMax[d], fc.smemBytes);
     ORBGPU_CUDA_CHECK(octree_configure(octMax[d]));
+    ORBGPU_CUDA_CHECK(octree_configure_lat(octMax[d]));
     ORBGPU_CUDA_CHECK(fast_configure(fastMax[d]));
   }
   e->T = T; e->ntiles = (int)tiles.size(); e->fastCfg = fc; e->fastMaps = fastMaps; e->octSmem = octSmem;
@@ -339,9 +340,10 @@ int run_extract_range(orbgpu_extractor *e, const uint8_t *dImages, int imgBase, 
     ORBGPU_CUDA_CHECK(launch_fill_borders(e->T, B, 1, imgBase, batch, s));
   }
   { StageTimer t(e, 1); ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->fastMaps, e->dTiles, e->ntiles, e->fastCfg, imgBase, batch, s)); }
-  { StageTimer t(e, 2); ORBGPU_CUDA_CHECK(launch_octree(e->T, B, imgBase, batch, e->octSmem, s)); }
+  const bool lat = batch <= kLatencyBatch;       // frame-at-a-time calls: few CTAs, give each more threads
+  { StageTimer t(e, 2); ORBGPU_CUDA_CHECK(lat ? launch_octree_lat(e->T, B, imgBase, batch, e->octSmem, s) : launch_octree(e->T, B, imgBase, batch, e->octSmem, s)); }
   { StageTimer t(e, 3); ORBGPU_CUDA_CHECK(launch_blur(e->T, B, e->blurMaps, e->dBlurTiles, e->nBlurTiles, imgBase, batch, s)); }
-  { StageTimer t(e, 4); ORBGPU_CUDA_CHECK(launch_describe(e->T, B, imgBase, batch, s)); }
+  { StageTimer t(e, 4); ORBGPU_CUDA_CHECK(lat ? launch_describe_lat(e->T, B, imgBase, batch, s) : launch_describe(e->T, B, imgBase, batch, s)); }
   return ORBGPU_OK;
 }
 
@@ -822,6 +824,7 @@ int orbgpu_stereo_match_device(orbgpu_extractor *L, orbgpu_extractor *R, int fir
     ORBGPU_CUDA_CHECK(cudaMalloc(&L->dSorted, n * sizeof(int)));
     ORBGPU_CUDA_CHECK(cudaMalloc(&L->dRowStart, (size_t)L->p.max_batch * (L->p.max_height + 2) * sizeof(int)));
     ORBGPU_CUDA_CHECK(stereo_configure(L->p.max_height + 1));
+    ORBGPU_CUDA_CHECK(stereo_configure_lat(L->p.max_height + 1));
   }
   if (R != L) {
     ORBGPU_CUDA_CHECK(cudaEventRecord(R->evDone, R->stream));
@@ -832,7 +835,7 @@ int orbgpu_stereo_match_device(orbgpu_extractor *L, orbgpu_extractor *R, int fir
   A.cntL = L->dKpCount; A.cntR = R->dKpCount; A.kpCapL = L->kpCap; A.kpCapR = R->kpCap;
   A.firstL = first_left; A.firstR = first_right; A.pairs = pairs; A.mbf = mbf; A.mb = mb;
   A.uRight = L->dURight; A.depth = L->dDepth; A.bestSad = L->dBestSad; A.rowStart = L->dRowStart; A.sorted = L->dSorted;
-  { StageTimer t(L, 5); ORBGPU_CUDA_CHECK(launch_stereo(L->T, L->dT, A, L->kpCap, L->stream)); }
+  { StageTimer t(L, 5); ORBGPU_CUDA_CHECK(pairs <= kLatencyBatch / 2 ? launch_stereo_lat(L->T, L->dT, A, L->kpCap, L->stream) : launch_stereo(L->T, L->dT, A, L->kpCap, L->stream)); }
   if (R != L) {   // the right handle must not overwrite its buffers before the match has read them
     ORBGPU_CUDA_CHECK(cudaEventRecord(L->evDone, L->stream));
     ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(R->stream, L->evDone, 0));

@@ -100,7 +100,19 @@ __device__ __forceinline__ void sincos_glibc(float y, float *sinp, float *cosp) 
   *cosp = sincos_poly(xs, x2, neg, (n & 1) == 0);
 }
 
-constexpr int kWarpsPerCta = 8;
+// This translation unit is compiled twice: as is (throughput shape) and through *_lat.cu with a second thread shape for
+// frame-at-a-time calls (a stereo pair keeps only 16-32 CTAs busy, so the latency build gives each more threads);
+// ORBGPU_VARIANT suffixes the exported launchers.
+#ifndef ORBGPU_VARIANT
+#define ORBGPU_VARIANT
+#endif
+#define ORBGPU_CAT2(a, b) a##b
+#define ORBGPU_CAT(a, b) ORBGPU_CAT2(a, b)
+#define VNAME(x) ORBGPU_CAT(x, ORBGPU_VARIANT)
+#ifndef ORBGPU_DESCRIBE_WARPS
+#define ORBGPU_DESCRIBE_WARPS 4
+#endif
+constexpr int kWarpsPerCta = ORBGPU_DESCRIBE_WARPS;
 constexpr int kPatchR = 18;                    // |rotated pattern coordinate| <= round(13 * sqrt 2) = 18 < EDGE_THRESHOLD
 constexpr int kPatchRows = 2 * kPatchR + 1;    // 37
 constexpr int kPatchWords = 10;                // 40 bytes per staged row: up to 3 alignment bytes + 37
@@ -217,7 +229,7 @@ k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, co
 
 }  // namespace
 
-cudaError_t launch_describe(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, cudaStream_t s) {
+cudaError_t VNAME(launch_describe)(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, cudaStream_t s) {
   static std::mutex mu;
   static bool ready[64] = {};
   {

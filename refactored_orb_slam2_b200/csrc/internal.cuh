@@ -136,6 +136,11 @@ cudaError_t launch_octree(const LevelTable &T, const ExtractBuffers &B, int imgB
                           cudaStream_t s);
 int hamming_dense_q(int nq);
 cudaError_t launch_describe(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, cudaStream_t s);
+// second thread shape of octree / describe / stereo for small batches (octree_lat.cu, describe_lat.cu, stereo_lat.cu)
+constexpr int kLatencyBatch = 16;
+cudaError_t launch_octree_lat(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, int smemBytes, cudaStream_t s);
+cudaError_t octree_configure_lat(int smemBytes);
+cudaError_t launch_describe_lat(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, cudaStream_t s);
 size_t octree_smem_bytes(int maxNodes);
 cudaError_t octree_configure(int smemBytes);
 cudaError_t fast_configure(int smemBytes);
@@ -155,6 +160,8 @@ struct StereoArgs {
 };
 cudaError_t stereo_configure(int rows);
 cudaError_t launch_stereo(const LevelTable &T, const LevelTable *dT, const StereoArgs &A, int maxKp, cudaStream_t s);
+cudaError_t stereo_configure_lat(int rows);
+cudaError_t launch_stereo_lat(const LevelTable &T, const LevelTable *dT, const StereoArgs &A, int maxKp, cudaStream_t s);
 
 struct Top2Rec { int d1, d2; long long idx; };   // 16 bytes, the shard exchange unit
 static_assert(sizeof(Top2Rec) == 16, "Top2Rec must be 16 bytes");

@@ -27,6 +27,15 @@ namespace orbgpu {
 
 namespace {
 
+// This translation unit is compiled twice: as is (throughput shape) and through *_lat.cu with a second thread shape for
+// frame-at-a-time calls (a stereo pair keeps only 16-32 CTAs busy, so the latency build gives each more threads);
+// ORBGPU_VARIANT suffixes the exported launchers.
+#ifndef ORBGPU_VARIANT
+#define ORBGPU_VARIANT
+#endif
+#define ORBGPU_CAT2(a, b) a##b
+#define ORBGPU_CAT(a, b) ORBGPU_CAT2(a, b)
+#define VNAME(x) ORBGPU_CAT(x, ORBGPU_VARIANT)
 #ifndef ORBGPU_OCTREE_THREADS
 #define ORBGPU_OCTREE_THREADS 256      // measured on B200 (KITTI batch): 128 -> 0.47 ms, 192 -> 0.41, 256 -> 0.34, 512 -> 0.40, 1024 -> 0.57
 #endif
@@ -343,17 +352,19 @@ k_octree(const LevelTable *__restrict__ T, const Cand *__restrict__ candAll, con
 
 }  // namespace
 
+#ifndef ORBGPU_VARIANT_IS_SECONDARY
 size_t octree_smem_bytes(int maxNodes) {
   int m2 = 1;
   while (m2 < maxNodes) m2 <<= 1;
   return (size_t)m2 * 8 + (size_t)maxNodes * (16 + 8 + 8 + 4 + 4 + 4 + 4 + 4 + 4);
 }
 
-cudaError_t octree_configure(int smemBytes) {
+#endif
+cudaError_t VNAME(octree_configure)(int smemBytes) {
   return cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
 }
 
-cudaError_t launch_octree(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, int smemBytes,
+cudaError_t VNAME(launch_octree)(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, int smemBytes,
                           cudaStream_t s) {
   int M = 0;
   for (int l = 0; l < T.nlevels; l++) M = max(M, T.lv[l].maxNodes);

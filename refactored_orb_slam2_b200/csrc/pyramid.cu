@@ -90,7 +90,13 @@ k_resize_level(const LevelTable *__restrict__ T, uint8_t *__restrict__ pyr, cons
 // read it (4 of 5 rows at scale 1.2).  Only the interior is produced here (words may spill garbage into the
 // apron bytes next to it); k_fill_borders writes every apron afterwards.
 namespace {
-constexpr int kRW = 128, kRH = 32, kResizeWarps = 4;
+#ifndef ORBGPU_RESIZE_RH
+#define ORBGPU_RESIZE_RH 16
+#endif
+#ifndef ORBGPU_RESIZE_WARPS
+#define ORBGPU_RESIZE_WARPS 4
+#endif
+constexpr int kRW = 128, kRH = ORBGPU_RESIZE_RH, kResizeWarps = ORBGPU_RESIZE_WARPS;
 
 __global__ void __launch_bounds__(kResizeWarps * 32)
 k_resize_tiles(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict__ T, const int2 *__restrict__ tabs,

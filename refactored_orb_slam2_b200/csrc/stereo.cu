@@ -31,7 +31,19 @@ __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const 
          __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
-constexpr int kWarps = 8;
+// This translation unit is compiled twice: as is (throughput shape) and through *_lat.cu with a second thread shape for
+// frame-at-a-time calls (a stereo pair keeps only 16-32 CTAs busy, so the latency build gives each more threads);
+// ORBGPU_VARIANT suffixes the exported launchers.
+#ifndef ORBGPU_VARIANT
+#define ORBGPU_VARIANT
+#endif
+#define ORBGPU_CAT2(a, b) a##b
+#define ORBGPU_CAT(a, b) ORBGPU_CAT2(a, b)
+#define VNAME(x) ORBGPU_CAT(x, ORBGPU_VARIANT)
+#ifndef ORBGPU_STEREO_WARPS
+#define ORBGPU_STEREO_WARPS 2
+#endif
+constexpr int kWarps = ORBGPU_STEREO_WARPS;
 
 // rowStart[pair][rows + 1], sorted[pair][kpCapR]: right keypoint indices grouped by (int)y
 __global__ void __launch_bounds__(256)
@@ -239,11 +251,11 @@ k_stereo_filter(StereoArgs A) {
 
 }  // namespace
 
-cudaError_t stereo_configure(int rows) {
+cudaError_t VNAME(stereo_configure)(int rows) {
   return cudaFuncSetAttribute(k_stereo_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (rows + 1) * (int)sizeof(int));
 }
 
-cudaError_t launch_stereo(const LevelTable &T, const LevelTable *dT, const StereoArgs &A, int maxKp, cudaStream_t s) {
+cudaError_t VNAME(launch_stereo)(const LevelTable &T, const LevelTable *dT, const StereoArgs &A, int maxKp, cudaStream_t s) {
   const int rows = T.lv[0].h;
   // a right keypoint at row yR reaches rows floor(yR - r) .. ceil(yR + r), r <= 2 * scale of the top level
   const int rowReach = (int)std::ceil(2.0f * T.lv[T.nlevels - 1].scale) + 2;

@@ -39,9 +39,9 @@ def test_stereo_pair_parity(pkg, w, h, nf, cam, seed):
     assert int((f.mvuRight >= 0).sum()) == kept
 
 
-def test_batched_pairs_one_handle(pkg):
+@pytest.mark.parametrize("npairs", [5, 11])        # <= 8 pairs run the latency thread shapes of octree / describe / stereo, more the throughput ones
+def test_batched_pairs_one_handle(pkg, npairs):
     """EuRoC-shaped pairs batched on one handle: left images first, right images after them."""
-    npairs = 5
     left, right = gen_synth.frame_batch(npairs, 480, 752, 1000, stereo=True)
     params = (1200, 1.2, 8, 20, 7)
     bf, fx = EUROC

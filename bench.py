@@ -306,7 +306,7 @@ def run_own(args, rank, local_rank, world):
     # ---- the reference's own calling pattern: ONE stereo pair per call (configs[1] as Tracking::GrabImageStereo runs it);
     # informational, the small-batch path replays a CUDA graph of the 13-kernel extraction sequence
     latency_ms = None
-    if rank == 0:
+    if rank == 0 and not args.no_latency:
         ex1 = pkg.ORBextractor(*PARAMS, max_width=W, max_height=H, max_batch=2, device=local_rank)
         cap1 = ex1.capacity
         pair = torch.stack([host[0], host[pairs]]).pin_memory()
@@ -477,6 +477,7 @@ def main():
     ap.add_argument("--hamming-exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the per-shard top-2 records travel: the library's peer-memory kernels (default) or one NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the informational single-pair latency loop (profiling runs)")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
     if world == 1 and args.gpus > 1:

@@ -654,7 +654,7 @@ int orbgpu_extract_batch_async(orbgpu_extractor *e, const uint8_t *images, int c
     for (auto &ev : e->evChunkDone) ORBGPU_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   }
   const size_t imgBytes = (size_t)width * height;
-  static const int wantChunks = [] { const char *v = getenv("ORBGPU_CHUNKS"); const int n = v ? atoi(v) : 4; return std::min(std::max(n, 1), (int)orbgpu_extractor::kMaxChunks); }();
+  static const int wantChunks = [] { const char *v = getenv("ORBGPU_CHUNKS"); const int n = v ? atoi(v) : 2; return std::min(std::max(n, 1), (int)orbgpu_extractor::kMaxChunks); }();   // measured with two batches in flight: 1 -> 68.7k, 2 -> 71.5k, 3 -> 70.2k, 4 -> 69.7k, 8 -> 63.0k frames/s
   const int chunks = count >= 8 * wantChunks ? wantChunks : count >= 16 ? 2 : 1;
   const int per = (count + chunks - 1) / chunks;
   const int cols = std::min(capacity, e->kpCap);

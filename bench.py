@@ -471,7 +471,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--pairs", type=int, default=160, help="stereo pairs per step per GPU (320 images = 149 MB > L2)")
+    ap.add_argument("--pairs", type=int, default=320, help="stereo pairs per step per GPU (640 images = 299 MB > L2)")
     ap.add_argument("--ref-pairs", type=int, default=0)
     ap.add_argument("--no-hamming", action="store_true")
     ap.add_argument("--hamming-exchange", default="peer", choices=["peer", "nccl"],

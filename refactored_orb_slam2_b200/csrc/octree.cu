@@ -127,7 +127,9 @@ k_octree(const LevelTable *__restrict__ T, const Cand *__restrict__ candAll, con
   __shared__ int sRootCnt[kMaxRoots], sRootPos[kMaxRoots];
   __shared__ int sSize, sNProc, sExpand;
 
-  const int level = blockIdx.x, img = imgBase + blockIdx.y;
+  // x = image, y = level: CTAs are issued x-fastest, so every level-0 CTA (the longest: most candidates, most rounds) starts
+  // before any level-7 one and the short ones fill the tail of the launch
+  const int level = blockIdx.y, img = imgBase + blockIdx.x;
   const LevelGeom &G = T->lv[level];
   const int tid = threadIdx.x;
   const int N = G.quota;
@@ -370,7 +372,7 @@ cudaError_t VNAME(launch_octree)(const LevelTable &T, const ExtractBuffers &B, i
   for (int l = 0; l < T.nlevels; l++) M = max(M, T.lv[l].maxNodes);
   int M2 = 1;
   while (M2 < M) M2 <<= 1;
-  dim3 grid(T.nlevels, batch);
+  dim3 grid(batch, T.nlevels);
   k_octree<<<grid, kThreads, smemBytes, s>>>(B.dT, B.cand, B.candCount, B.nodeOf, B.sel, B.selCount, B.status, M, M2, imgBase);
   count_launch();
   return cudaGetLastError();

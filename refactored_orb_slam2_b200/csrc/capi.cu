@@ -88,6 +88,9 @@ struct orbgpu_extractor {
   // stereo results (owned by the LEFT handle)
   float *dURight = nullptr, *dDepth = nullptr; int *dBestSad = nullptr, *dRowStart = nullptr, *dSorted = nullptr;
   cudaEvent_t evDone = nullptr;
+  // the blur of a batch only needs its pyramid: it runs on a side stream next to FAST + octree and joins before describe
+  cudaStream_t side = nullptr;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
   int lastBatch = 0;
   // CUDA graph of the extraction kernel sequence for small batches (the frame-at-a-time path is launch bound: 13 kernels
   // and 2 memsets for one stereo pair); re-captured whenever its key changes
@@ -328,19 +331,45 @@ int run_extract_range(orbgpu_extractor *e, const uint8_t *dImages, int imgBase, 
   cudaStream_t s = e->stream;
   ORBGPU_CUDA_CHECK(cudaMemsetAsync(e->dCandCount + (size_t)imgBase * kMaxLevels, 0, sizeof(int) * kMaxLevels * batch, s));
   ORBGPU_CUDA_CHECK(cudaMemsetAsync(e->dSelCount + (size_t)imgBase * kMaxLevels, 0, sizeof(int) * kMaxLevels * batch, s));
+  // Two streams per batch: the blur only needs the pyramid, so it runs on a side stream next to FAST and the octree and joins
+  // before the descriptor kernel.  FAST is bound by the ALU pipe, the blur by issue slots, the octree by latency: the blur fills
+  // FAST's tail and the octree's idle slots (+5 % frames/s).  (Also moving the pyramid chain of levels 1 .. 7 to the side stream
+  // with FAST split into level 0 / the rest was measured and gives nothing more: those kernels compete for the same issue slots.)
+  // With per-stage timing on, everything stays on one stream so that the stage timers remain meaningful.
+  static const bool noOverlap = getenv("ORBGPU_NO_OVERLAP") != nullptr;
+  const bool overlap = !noOverlap && !e->profiling;
+  const bool lat = batch <= kLatencyBatch;       // frame-at-a-time calls: few CTAs, give each more threads
+  auto pyramid_rest = [&](cudaStream_t q) -> int {
+    for (int l = 1; l < e->T.nlevels; l++) {
+      if (e->T.lv[l].rzBoxW)
+        ORBGPU_CUDA_CHECK(launch_resize_tiles(e->T, B, e->rzMaps, e->dRzTiles + e->rzTileOff[l], e->rzTileCnt[l], e->rzSlotBytes, imgBase, batch, q));
+      else
+        ORBGPU_CUDA_CHECK(launch_resize_level(e->T, B, l, imgBase, batch, q));
+    }
+    ORBGPU_CUDA_CHECK(launch_fill_borders(e->T, B, 1, imgBase, batch, q));
+    return ORBGPU_OK;
+  };
+  if (overlap) {
+    ORBGPU_CUDA_CHECK(launch_import_level0(e->T, B, dImages, rowStep, imgStep, imgBase, batch, s));
+    int rc = pyramid_rest(s);
+    if (rc) return rc;
+    ORBGPU_CUDA_CHECK(cudaEventRecord(e->evFork, s));
+    ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(e->side, e->evFork, 0));
+    ORBGPU_CUDA_CHECK(launch_blur(e->T, B, e->blurMaps, e->dBlurTiles, e->nBlurTiles, imgBase, batch, e->side));
+    ORBGPU_CUDA_CHECK(cudaEventRecord(e->evJoin, e->side));
+    ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->fastMaps, e->dTiles, e->ntiles, e->fastCfg, imgBase, batch, s));
+    ORBGPU_CUDA_CHECK(lat ? launch_octree_lat(e->T, B, imgBase, batch, e->octSmem, s) : launch_octree(e->T, B, imgBase, batch, e->octSmem, s));
+    ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(s, e->evJoin, 0));
+    ORBGPU_CUDA_CHECK(lat ? launch_describe_lat(e->T, B, imgBase, batch, s) : launch_describe(e->T, B, imgBase, batch, s));
+    return ORBGPU_OK;
+  }
   {
     StageTimer t(e, 0);
     ORBGPU_CUDA_CHECK(launch_import_level0(e->T, B, dImages, rowStep, imgStep, imgBase, batch, s));
-    for (int l = 1; l < e->T.nlevels; l++) {
-      if (e->T.lv[l].rzBoxW)
-        ORBGPU_CUDA_CHECK(launch_resize_tiles(e->T, B, e->rzMaps, e->dRzTiles + e->rzTileOff[l], e->rzTileCnt[l], e->rzSlotBytes, imgBase, batch, s));
-      else
-        ORBGPU_CUDA_CHECK(launch_resize_level(e->T, B, l, imgBase, batch, s));
-    }
-    ORBGPU_CUDA_CHECK(launch_fill_borders(e->T, B, 1, imgBase, batch, s));
+    int rc = pyramid_rest(s);
+    if (rc) return rc;
   }
   { StageTimer t(e, 1); ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->fastMaps, e->dTiles, e->ntiles, e->fastCfg, imgBase, batch, s)); }
-  const bool lat = batch <= kLatencyBatch;       // frame-at-a-time calls: few CTAs, give each more threads
   { StageTimer t(e, 2); ORBGPU_CUDA_CHECK(lat ? launch_octree_lat(e->T, B, imgBase, batch, e->octSmem, s) : launch_octree(e->T, B, imgBase, batch, e->octSmem, s)); }
   { StageTimer t(e, 3); ORBGPU_CUDA_CHECK(launch_blur(e->T, B, e->blurMaps, e->dBlurTiles, e->nBlurTiles, imgBase, batch, s)); }
   { StageTimer t(e, 4); ORBGPU_CUDA_CHECK(lat ? launch_describe_lat(e->T, B, imgBase, batch, s) : launch_describe(e->T, B, imgBase, batch, s)); }
@@ -483,6 +512,9 @@ int orbgpu_extractor_create(const orbgpu_extractor_params *params, orbgpu_extrac
 
   ORBGPU_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   ORBGPU_CUDA_CHECK(cudaEventCreateWithFlags(&e->evDone, cudaEventDisableTiming));
+  ORBGPU_CUDA_CHECK(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+  ORBGPU_CUDA_CHECK(cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming));
+  ORBGPU_CUDA_CHECK(cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming));
   LevelTable T;
   std::vector<int2> tabs;
   std::vector<int4> tiles;
@@ -521,6 +553,9 @@ void orbgpu_extractor_destroy(orbgpu_extractor *e) {
   for (void *q : ptrs) if (q) cudaFree(q);
   if (e->graph.exec) cudaGraphExecDestroy(e->graph.exec);
   if (e->evDone) cudaEventDestroy(e->evDone);
+  if (e->evFork) cudaEventDestroy(e->evFork);
+  if (e->evJoin) cudaEventDestroy(e->evJoin);
+  if (e->side) cudaStreamDestroy(e->side);
   for (cudaEvent_t ev : e->evChunkIn) if (ev) cudaEventDestroy(ev);
   for (cudaEvent_t ev : e->evChunkDone) if (ev) cudaEventDestroy(ev);
   if (e->copyIn) cudaStreamDestroy(e->copyIn);

@@ -669,8 +669,11 @@ int orbgpu_download_results(orbgpu_extractor *e, orbgpu_keypoint *keypoints, uin
 
 // Host-buffer form.  Large batches are cut into chunks that flow through three streams — H2D copy, the kernel
 // sequence, D2H copy — so that the PCIe transfers of chunks k+1 / k-1 overlap the kernels of chunk k.
-int orbgpu_extract_batch_async(orbgpu_extractor *e, const uint8_t *images, int count, int width, int height, size_t row_step,
-                               size_t image_step, orbgpu_keypoint *keypoints, uint8_t *descriptors, int capacity, int32_t *counts) {
+// chunkScale: the synchronous call hides its first upload / last download better with more, smaller chunks (x2); callers that
+// keep several batches in flight already overlap neighbouring batches and prefer fewer, larger ones
+static int enqueue_extract_batch(orbgpu_extractor *e, const uint8_t *images, int count, int width, int height, size_t row_step,
+                                 size_t image_step, orbgpu_keypoint *keypoints, uint8_t *descriptors, int capacity, int32_t *counts,
+                                 int chunkScale) {
   if (!e || !images || !counts) { set_error("null argument"); return ORBGPU_E_INVALID; }
   if (count < 1 || count > e->p.max_batch) { set_error("batch %d outside 1..%d", count, e->p.max_batch); return ORBGPU_E_CAPACITY; }
   if (width < 1 || height < 1 || row_step < (size_t)width) { set_error("bad image shape"); return ORBGPU_E_INVALID; }
@@ -690,7 +693,8 @@ int orbgpu_extract_batch_async(orbgpu_extractor *e, const uint8_t *images, int c
   }
   const size_t imgBytes = (size_t)width * height;
   static const int wantChunks = [] { const char *v = getenv("ORBGPU_CHUNKS"); const int n = v ? atoi(v) : 2; return std::min(std::max(n, 1), (int)orbgpu_extractor::kMaxChunks); }();   // measured with two batches in flight: 1 -> 68.7k, 2 -> 71.5k, 3 -> 70.2k, 4 -> 69.7k, 8 -> 63.0k frames/s
-  const int chunks = count >= 8 * wantChunks ? wantChunks : count >= 16 ? 2 : 1;
+  const int want = std::min(wantChunks * chunkScale, (int)orbgpu_extractor::kMaxChunks);
+  const int chunks = count >= 8 * want ? want : count >= 16 ? 2 : 1;
   const int per = (count + chunks - 1) / chunks;
   const int cols = std::min(capacity, e->kpCap);
   begin_batch(e);
@@ -737,6 +741,11 @@ int orbgpu_extract_batch_async(orbgpu_extractor *e, const uint8_t *images, int c
   return ORBGPU_OK;
 }
 
+int orbgpu_extract_batch_async(orbgpu_extractor *e, const uint8_t *images, int count, int width, int height, size_t row_step,
+                               size_t image_step, orbgpu_keypoint *keypoints, uint8_t *descriptors, int capacity, int32_t *counts) {
+  return enqueue_extract_batch(e, images, count, width, height, row_step, image_step, keypoints, descriptors, capacity, counts, 1);
+}
+
 int orbgpu_wait(orbgpu_extractor *e) {
   if (!e) { set_error("null handle"); return ORBGPU_E_INVALID; }
   DeviceGuard guard(e->device);
@@ -753,7 +762,7 @@ int orbgpu_wait(orbgpu_extractor *e) {
 
 int orbgpu_extract_batch(orbgpu_extractor *e, const uint8_t *images, int count, int width, int height, size_t row_step,
                          size_t image_step, orbgpu_keypoint *keypoints, uint8_t *descriptors, int capacity, int32_t *counts) {
-  int rc = orbgpu_extract_batch_async(e, images, count, width, height, row_step, image_step, keypoints, descriptors, capacity, counts);
+  int rc = enqueue_extract_batch(e, images, count, width, height, row_step, image_step, keypoints, descriptors, capacity, counts, 2);
   if (rc) return rc;
   return orbgpu_wait(e);
 }

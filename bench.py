@@ -428,7 +428,7 @@ def run_own(args, rank, local_rank, world):
         if not args.no_cpu_baseline:
             stereo_batch, kind, cpu_host = cpu_reference()
             cores = os.cpu_count() or 1
-            sample_pairs = min(pairs, max(16, min(160, 4 * cores)))
+            sample_pairs = min(pairs, max(16, min(320, 12 * cores)))      # ~1 s of wall clock = 10-30 s of CPU work
             hl = host.numpy()
             stereo_batch(PARAMS, hl[:min(cores, sample_pairs)], hl[pairs:pairs + min(cores, sample_pairs)], BF, np.float32(mb), cores)   # warm
             t0 = time.perf_counter()

@@ -74,10 +74,10 @@ __device__ __forceinline__ unsigned margin_of_ring(const unsigned (&d)[16], unsi
 struct TileGeom {
   int level, img, X0, Y0, TW, TH, gx0, offL, groups, bx, lead;
 };
-__device__ __forceinline__ TileGeom tile_geom(const LevelTable *T, const int4 *tiles, int ntiles, int item, int imgBase) {
+// (ti, img) = tile index within an image and image of the work item; the caller steps them without dividing
+__device__ __forceinline__ TileGeom tile_geom(const LevelTable *T, const int4 *tiles, int ti, int img) {
   TileGeom t;
-  const int ti = item % ntiles;
-  t.img = imgBase + item / ntiles;
+  t.img = img;
   const int4 tile = tiles[ti];                            // (level, cell row i, first cell column j0, cell count)
   t.level = tile.x;
   const LevelGeom &G = T->lv[t.level];
@@ -125,15 +125,20 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
   }
   __syncthreads();
   if (tid == 0 && (int)blockIdx.x < totalItems) {
-    const TileGeom n = tile_geom(T, tiles, ntiles, blockIdx.x, imgBase);
+    const TileGeom n = tile_geom(T, tiles, (int)blockIdx.x % ntiles, imgBase + (int)blockIdx.x / ntiles);
     const LevelGeom &Gn = T->lv[n.level];
     mbar_expect_tx(&sBar, (unsigned)(Gn.fastBoxW * Gn.fastBoxH));
     tma_load_3d(smem, &maps.m[n.level], n.bx, n.Y0 - 3 + kEdge, n.img, &sBar);
   }
+  // work item = (tile ti of image imgCur); stepping by gridDim.x items without a division per tile
+  int ti = (int)blockIdx.x % ntiles, imgCur = imgBase + (int)blockIdx.x / ntiles;
+  const int stepImg = (int)gridDim.x / ntiles, stepTi = (int)gridDim.x - stepImg * ntiles;
 
   int iter = 0;
   for (int item = blockIdx.x; item < totalItems; item += gridDim.x, iter++) {
-    const TileGeom tg = tile_geom(T, tiles, ntiles, item, imgBase);
+    const TileGeom tg = tile_geom(T, tiles, ti, imgCur);
+    int tiNext = ti + stepTi, imgNext = imgCur + stepImg;
+    if (tiNext >= ntiles) { tiNext -= ntiles; imgNext++; }
     const LevelGeom &G = T->lv[tg.level];
     const int level = tg.level, img = tg.img, X0 = tg.X0, Y0 = tg.Y0, TW = tg.TW, TH = tg.TH;
     const int offL = tg.offL, groups = tg.groups, lead = tg.lead;
@@ -163,7 +168,7 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
     if (tid == 0) {
       const int next = item + gridDim.x;
       if (next < totalItems) {
-        const TileGeom n = tile_geom(T, tiles, ntiles, next, imgBase);
+        const TileGeom n = tile_geom(T, tiles, tiNext, imgNext);
         const LevelGeom &Gn = T->lv[n.level];
         mbar_expect_tx(&sBar, (unsigned)(Gn.fastBoxW * Gn.fastBoxH));
         tma_load_3d(smem, &maps.m[n.level], n.bx, n.Y0 - 3 + kEdge, n.img, &sBar);
@@ -293,6 +298,7 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
     }
   }
     __syncthreads();   // stage list (= plane A), queue and counters are free again
+    ti = tiNext; imgCur = imgNext;
   }
 }
 

@@ -291,18 +291,20 @@ def run_own(args, rank, local_rank, world):
     # the same calls, two batches in flight (pkg.StereoBatchPipeline: two handles, split async / wait entry points, one host thread), so that one
     # batch uploads while the other computes; every batch is copied in from pinned host memory and its results copied out
     del out_k, out_d, out_c, out_u, out_z
-    pipe = pkg.StereoBatchPipeline(PARAMS, W, H, pairs, BF, mb, depth=2, device=local_rank)
-    for _ in range(2):
+    depth = max(2, env_int("BENCH_PIPELINE_DEPTH", 2))
+    pipe = pkg.StereoBatchPipeline(PARAMS, W, H, pairs, BF, mb, depth=depth, device=local_rank)
+    for _ in range(depth):
         pipe.submit(host)
-    for _ in range(2):
+    for _ in range(depth):
         pipe.result()
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        if i >= 2:
-            pipe.result()          # batch i - 2: frees its handle; batch i - 1 is still in flight while batch i is enqueued
+        if i >= depth:
+            pipe.result()          # batch i - depth: frees its handle; the batches after it are still in flight while batch i is enqueued
         pipe.submit(host)
-    pipe.result()
+    for _ in range(min(depth, args.steps) - 1):
+        pipe.result()
     last = pipe.result()
     torch.cuda.synchronize()
     dt = max_over_ranks(time.perf_counter() - t0)
@@ -448,7 +450,7 @@ def run_own(args, rank, local_rank, world):
                        "host_numa_node_rank0": numa_node},
             "clocks": clocks,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "StereoBatchPipeline(depth=2) over orbgpu_extract_batch_async + orbgpu_stereo_match_async + orbgpu_wait, pinned host buffers",
+                    "api": "StereoBatchPipeline(depth=%d) over orbgpu_extract_batch_async + orbgpu_stereo_match_async + orbgpu_wait, pinned host buffers" % depth,
                     "single_pair_latency_ms": latency_ms,
                     "single_call_value": world * nimg * args.steps / dt_sync},
             "gpu_launches": launches,

@@ -44,6 +44,20 @@ def test_no_cpu_fallback(built):
         pkg.DescriptorBank(np.zeros((4, 32), np.uint8))
     with pytest.raises(pkg.OrbGpuError):
         pkg.ORBmatcher.DescriptorDistance(np.zeros(32, np.uint8), np.zeros(32, np.uint8))
+    # the widened rows have no CPU path either: feature sets / searches, vocabulary descent, staging, distinctive descriptors,
+    # the sharded-bank exchange
+    kp = np.zeros(3, pkg.KP_DTYPE)
+    for call in (lambda: pkg.FrameFeatures(kp, np.zeros((3, 32), np.uint8), None, pkg.grid_geometry(0.0, 640.0, 0.0, 480.0)),
+                 lambda: pkg.Vocabulary([0, 2, 2, 2], [1, 2], np.zeros((3, 32), np.uint8), [-1, 0, 1], 1),
+                 lambda: pkg.staging.cvtColorGray(np.zeros((4, 4, 3), np.uint8)),
+                 lambda: pkg.staging.remap(np.zeros((4, 4), np.uint8), np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32)),
+                 lambda: pkg.distinctive_descriptors(np.zeros((3, 32), np.uint8), [0, 3])):
+        with pytest.raises(pkg.OrbGpuError) as e:
+            call()
+        assert e.value.code == -2
+    import ctypes as C
+    out, handle = C.c_void_p(), np.zeros(64, np.uint8)
+    assert pkg.lib().orbgpu_exchange_create(0, 1, 16, -1, C.byref(out), handle.ctypes.data_as(C.c_void_p)) == -2
 
 
 def test_product_does_not_import_oracle():

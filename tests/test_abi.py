@@ -90,3 +90,26 @@ def test_host_policy_matches_oracle(built):
     a1 = rng.uniform(0, 360, 500).astype(np.float32)
     a2 = np.where(rng.random(500) < 0.7, a1 - 20, rng.uniform(0, 360, 500)).astype(np.float32) % np.float32(360)
     assert np.array_equal(pkg.ORBmatcher.rotation_consistent(a1, a2), oracle.rotation_filter(a1, a2))
+
+
+def test_bench_own_arm_does_not_touch_the_oracle():
+    """bench.py may reach into oracle/ only from the CPU-baseline leg (cpu_reference): nowhere else may it import the oracle
+    modules or put oracle/ on sys.path."""
+    import ast
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    oracle_modules = {"oracle", "ref", "gen_synth", "oracle_cv2", "slam_ref", "slam_scenarios", "voc_ref"}
+    offenders = []
+    for fn in ast.walk(tree):
+        if isinstance(fn, (ast.FunctionDef, ast.Module)):
+            for node in (fn.body if isinstance(fn, ast.Module) else ast.walk(fn)):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name.split(".")[0] for a in node.names]
+                elif isinstance(node, ast.ImportFrom) and node.module:
+                    names = [node.module.split(".")[0]]
+                for n in names:
+                    if n in oracle_modules and not (isinstance(fn, ast.FunctionDef) and fn.name == "cpu_reference"):
+                        offenders.append((getattr(fn, "name", "<module>"), n))
+    assert not offenders, offenders
+    assert src.count('os.path.join(ROOT, "oracle")') == 1      # the sys.path entry is added inside cpu_reference only

@@ -25,9 +25,8 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 }
 
 __global__ void __launch_bounds__(256)
-k_import_level0(const LevelTable *__restrict__ T, uint8_t *__restrict__ pyr, const uint8_t *__restrict__ src,
-                size_t rowStep, size_t imgStep, int imgBase) {
-  const LevelGeom &G = T->lv[0];
+k_import_level0(const __grid_constant__ LevelGeom G, uint8_t *__restrict__ pyr, const uint8_t *__restrict__ src,
+                size_t rowStep, size_t imgStep, int imgBase) {   // level-0 geometry by value: no dependent table loads in front of the copy
   const int img = imgBase + blockIdx.z;
   const int py = blockIdx.y * blockDim.y + threadIdx.y;
   const int px4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -212,7 +211,7 @@ static dim3 plane_grid(const LevelGeom &G, int batch, dim3 block) {
 cudaError_t launch_import_level0(const LevelTable &T, const ExtractBuffers &B, const uint8_t *src,
                                  size_t rowStep, size_t imgStep, int imgBase, int batch, cudaStream_t s) {
   dim3 block(64, 4);
-  k_import_level0<<<plane_grid(T.lv[0], batch, block), block, 0, s>>>(B.dT, B.pyr, src, rowStep, imgStep, imgBase);
+  k_import_level0<<<plane_grid(T.lv[0], batch, block), block, 0, s>>>(T.lv[0], B.pyr, src, rowStep, imgStep, imgBase);
   count_launch();
   return cudaGetLastError();
 }

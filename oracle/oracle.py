@@ -111,7 +111,8 @@ class OracleExtractor:
 
     @property
     def capacity(self):
-        return self.nfeatures + 3 * self.nlevels + 64
+        # a level can return 4 x (octree roots) keypoints even when its quota is smaller (wide images, small nfeatures)
+        return self.nfeatures + 3 * self.nlevels + 64 * self.nlevels
 
     def __call__(self, image, mask=None):
         img = np.ascontiguousarray(image, np.uint8)

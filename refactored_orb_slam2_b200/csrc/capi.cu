@@ -507,7 +507,9 @@ int orbgpu_extractor_create(const orbgpu_extractor_params *params, orbgpu_extrac
   }
   e->quota[nl - 1] = std::max(p.nfeatures - sum, 0);
   int cap = 0;
-  for (int l = 0; l < nl; l++) cap += std::max(e->quota[l] + 3, 16);
+  // a level returns at most max(quota + 3, 4 * roots) keypoints: the octree stops within one split of its quota, but never
+  // before the first round has split every root (ORBextractor.cc:566-745), and a level has up to kMaxRoots roots
+  for (int l = 0; l < nl; l++) cap += std::max(e->quota[l] + 3, 4 * kMaxRoots);
   e->kpCap = (int)round_up(cap, 8);
 
   ORBGPU_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));

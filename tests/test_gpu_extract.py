@@ -32,6 +32,9 @@ CONFIGS = [
     ("odd_small", 301, 227, 150, 6, "texture"),         # top level 84x63: one cell row, 1 root, tiny quotas
     ("flat", 320, 240, 500, 0, "flat"),                 # no corners anywhere: empty output
     ("few", 400, 300, 4000, 8, "texture"),              # quota far above the candidate count
+    ("binary", 341, 263, 400, 9, "binary"),             # 0 / 255 only: arc margins at the ends of the packed 16-bit range
+    ("low_contrast", 310, 222, 400, 10, "low_contrast"),  # grey levels 100..118: margins sit right at minThFAST / iniThFAST
+    ("panorama", 1600, 260, 120, 12, "texture"),        # 7-10 octree roots per level: every level returns 4 x roots > its quota
 ]
 
 
@@ -40,6 +43,12 @@ def make_image(w, h, seed, kind):
         return gen_synth.texture(h, w, seed)
     if kind == "noise":
         return np.random.default_rng(seed).integers(0, 256, (h, w), dtype=np.uint8)
+    if kind == "binary":
+        return (np.random.default_rng(seed).integers(0, 2, (h, w)) * 255).astype(np.uint8)
+    if kind == "low_contrast":
+        rng = np.random.default_rng(seed)
+        base = rng.integers(100, 119, (h // 3 + 1, w // 3 + 1))
+        return np.kron(base, np.ones((3, 3), np.int64))[:h, :w].astype(np.uint8)
     return np.full((h, w), 117, np.uint8)
 
 

@@ -75,8 +75,9 @@ void orbgpu_extractor_destroy(orbgpu_extractor *e);
  * pointer may be NULL. */
 int orbgpu_extractor_tables(const orbgpu_extractor *e, float *scale, float *inv_scale, float *sigma2,
                             float *inv_sigma2, int32_t *features_per_level);
-/* Upper bound on keypoints per image: sum of per-level quotas + 3 per level (a careful octree split
- * adds at most 3 nodes before the >= N break, src/ORBextractor.cc:701-702). */
+/* Upper bound on keypoints per image: per level max(quota + 3, 4 x 16 roots) — a careful octree split adds at
+ * most 3 nodes before the >= N break (src/ORBextractor.cc:701-702), and the first round splits every root
+ * whatever the quota (src/ORBextractor.cc:566-600), so a wide level with a small quota returns 4 x roots. */
 int orbgpu_extractor_capacity(const orbgpu_extractor *e);
 
 /* ORBextractor::operator()(image, mask, keypoints, descriptors) (src/ORBextractor.cc:978-1039):

@@ -174,8 +174,9 @@ int build_table(const orbgpu_extractor &e, int w, int h, int batchCap, LevelTabl
       G.rootX1[i] = (int)(G.hX * (float)(i + 1));
     }
     G.maxNodes = std::max(G.quota, 4 * G.nIni) + 8;
-    const size_t detPix = (size_t)(G.w - 2 * kEdge) * (G.h - 2 * kEdge);
-    G.candCap = (int)round_up(detPix / 6 + 256, 64);
+    // NMS survivors are strict 8-neighbour maxima inside one cell's detection rectangle: at most ceil(cw / 2) * ceil(ch / 2)
+    // per cell, so (W / 2 + nCols) * (H / 2 + nRows) bounds a level whatever the image (W x H = the cells' union)
+    G.candCap = (int)round_up((size_t)((int)width / 2 + G.nCols + 1) * ((int)height / 2 + G.nRows + 1), 64);
     G.candOffset = candOff;
     candOff += (size_t)G.candCap * batchCap;
     G.selCap = (int)round_up(std::max(G.quota, 4 * G.nIni) + 4, 4);

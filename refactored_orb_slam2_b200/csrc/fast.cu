@@ -331,7 +331,7 @@ FastConfig fast_make_config(const LevelTable &T) {
   c.imgBytes = (img + 4 + 127) & ~127;               // + the word the unpack reads past the last one
   c.scorePitch = (tw + 3 + 3 + 3) & ~3;             // + the group overhang on both sides
   c.scoreBytes = (c.scorePitch * (hMax + 2) + 8 + 15) & ~15;   // + halo rows and the 4-byte lead of the halo column
-  c.stageCap = (tw / 2 + 1) * (hMax / 2 + 1);      // bound on strict 8-neighbour maxima in a tile
+  c.stageCap = (tw / 2 + kFastCellsPerTile) * (hMax / 2 + 1);   // strict 8-neighbour maxima per cell rectangle: ceil(cw / 2) * ceil(ch / 2)
   c.queueCap = c.scorePitch * hMax;
   // window + two u16 planes (the stage list lives in plane A) + scores + queue
   if (c.stageCap * (int)sizeof(Cand) > 2 * c.imgBytes) c.stageCap = 2 * c.imgBytes / (int)sizeof(Cand);

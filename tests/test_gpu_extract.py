@@ -35,6 +35,7 @@ CONFIGS = [
     ("binary", 341, 263, 400, 9, "binary"),             # 0 / 255 only: arc margins at the ends of the packed 16-bit range
     ("low_contrast", 310, 222, 400, 10, "low_contrast"),  # grey levels 100..118: margins sit right at minThFAST / iniThFAST
     ("panorama", 1600, 260, 120, 12, "texture"),        # 7-10 octree roots per level: every level returns 4 x roots > its quota
+    ("dot_lattice", 341, 263, 500, 0, "dot_lattice"),   # isolated dots every 2 px on a ramp: 21 % of level 0 survives NMS
 ]
 
 
@@ -45,6 +46,11 @@ def make_image(w, h, seed, kind):
         return np.random.default_rng(seed).integers(0, 256, (h, w), dtype=np.uint8)
     if kind == "binary":
         return (np.random.default_rng(seed).integers(0, 2, (h, w)) * 255).astype(np.uint8)
+    if kind == "dot_lattice":
+        img = np.zeros((h, w), np.uint8)
+        ii, jj = np.meshgrid(np.arange(0, w, 2) // 2, np.arange(0, h, 2) // 2)
+        img[::2, ::2] = (50 + (ii * 24 + jj) % 192).astype(np.uint8)
+        return img
     if kind == "low_contrast":
         rng = np.random.default_rng(seed)
         base = rng.integers(100, 119, (h // 3 + 1, w // 3 + 1))

@@ -54,6 +54,39 @@ def test_batched_pairs_one_handle(pkg, npairs):
         assert np.array_equal(u[i, :n], ou) and np.array_equal(z[i, :n], oz), "pair %d" % i
 
 
+def test_stereo_edge_cases_in_one_batch(pkg):
+    """Pairs with no right keypoints, with no left keypoints, a 2-px dot lattice (crowded row buckets, many equal descriptors
+    distances) and 0 / 255 noise, batched on one handle: every pair equals the oracle and the empty ones do not disturb the rest."""
+    h, w = 263, 341
+    def lattice(width):
+        img = np.zeros((h, width), np.uint8)
+        ii, jj = np.meshgrid(np.arange(0, width, 2) // 2, np.arange(0, h, 2) // 2)
+        img[::2, ::2] = (50 + (ii * 24 + jj) % 192).astype(np.uint8)
+        return img
+    tex, flat = gen_synth.texture(h, w, 3), np.full((h, w), 90, np.uint8)
+    lat = lattice(w + 6)
+    noise = (np.random.default_rng(4).integers(0, 2, (h, w + 10)) * 255).astype(np.uint8)
+    pairs = [(tex, flat), (flat, tex), (lat[:, :-6], lat[:, 6:]), (noise[:, :-10], noise[:, 10:])]
+    left = np.stack([np.ascontiguousarray(p[0]) for p in pairs])
+    right = np.stack([np.ascontiguousarray(p[1]) for p in pairs])
+    params = (500, 1.2, 8, 20, 7)
+    bf, fx = KITTI
+    g = pkg.ORBextractor(*params, max_width=w, max_height=h, max_batch=2 * len(pairs))
+    kps, desc, counts = g.extract_batch(np.concatenate([left, right]))
+    u, z = pkg.ComputeStereoMatches(g, g, bf, np.float32(bf) / np.float32(fx), first_left=0, first_right=len(pairs), pairs=len(pairs))
+    matched = []
+    for i in range(len(pairs)):
+        n, ou, oz, kept = oracle_pair(params, left[i], right[i], bf, fx)
+        assert counts[i] == n
+        assert np.array_equal(u[i, :n], ou) and np.array_equal(z[i, :n], oz), "pair %d" % i
+        matched.append(kept)
+    assert matched[0] == 0 and matched[1] == 0 and matched[2] > 100 and matched[3] > 40
+    # the reference's constructor shape (one pair per call) on the empty cases
+    for l, r in pairs[:2]:
+        f = pkg.Frame(l, r, pkg.ORBextractor(*params), pkg.ORBextractor(*params), bf, fx)
+        assert (f.mvuRight == -1).all() and (f.mvDepth == -1).all() and len(f.mvuRight) == f.N
+
+
 def test_integer_shift_recovers_disparity(pkg):
     """Size-independent property: right = left shifted by d px  =>  uL - uR ~= d for the matches."""
     d = 23

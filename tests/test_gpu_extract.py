@@ -95,7 +95,10 @@ def test_kitti_thresholds_variant(pkg):
 
 def test_other_pyramid_parameters(pkg):
     img = gen_synth.texture(480, 640, 21)
-    for params in [(800, 1.5, 4, 25, 10), (1500, 1.1, 12, 20, 7), (300, 2.0, 3, 30, 5)]:
+    # 1 and 2 levels, a 1.05 pyramid, iniThFAST == minThFAST (the fallback never adds anything), thresholds 40 / 39
+    # (a handful of keypoints: iniS = 1 in the kernel's score units)
+    for params in [(800, 1.5, 4, 25, 10), (1500, 1.1, 12, 20, 7), (300, 2.0, 3, 30, 5), (500, 1.2, 1, 20, 7), (700, 1.2, 2, 20, 7),
+                   (1000, 1.05, 8, 20, 7), (600, 1.2, 8, 7, 7), (600, 1.2, 8, 40, 39)]:
         ok, od = oracle.OracleExtractor(*params)(img)
         gk, gd = pkg.ORBextractor(*params)(img)
         assert_same_keypoints(gk, gd, ok, od)

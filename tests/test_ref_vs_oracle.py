@@ -49,6 +49,39 @@ def test_noise_image_many_ties():
     assert np.array_equal(rd, d) and np.array_equal(rk["x"], k["x"]) and np.array_equal(rk["y"], k["y"])
 
 
+def _adversarial(kind, w, h, seed):
+    if kind == "binary":
+        return (np.random.default_rng(seed).integers(0, 2, (h, w)) * 255).astype(np.uint8)
+    if kind == "dot_lattice":            # isolated dots every 2 px on a ramp: a fifth of level 0 survives NMS
+        img = np.zeros((h, w), np.uint8)
+        ii, jj = np.meshgrid(np.arange(0, w, 2) // 2, np.arange(0, h, 2) // 2)
+        img[::2, ::2] = (50 + (ii * 24 + jj) % 192).astype(np.uint8)
+        return img
+    if kind == "low_contrast":           # grey levels 100..118 in 3x3 blocks: margins right at the two thresholds
+        base = np.random.default_rng(seed).integers(100, 119, (h // 3 + 1, w // 3 + 1))
+        return np.kron(base, np.ones((3, 3), np.int64))[:h, :w].astype(np.uint8)
+    return gen_synth.texture(h, w, seed)
+
+
+@pytest.mark.parametrize("kind,w,h,nf,seed", [("binary", 341, 263, 400, 9), ("dot_lattice", 341, 263, 500, 0),
+                                              ("low_contrast", 310, 222, 400, 10), ("panorama", 1600, 260, 120, 12)])
+def test_reference_code_equals_oracle_on_adversarial_images(kind, w, h, nf, seed):
+    """The inputs of the GPU parity cases of the same names: the oracle they are checked against is itself the reference's
+    code here (panorama: 7-10 octree roots per level, every level returns 4 x roots keypoints, more than its quota)."""
+    img = _adversarial(kind, w, h, seed)
+    o = oracle.OracleExtractor(nf)
+    k, d = o(img)
+    rk, rd = ref.ReferenceExtractor(nf)(img)
+    assert len(rk) == len(k) > 0
+    for f in k.dtype.names:
+        assert np.array_equal(rk[f], k[f]), f
+    assert np.array_equal(rd, d)
+    if kind == "panorama":
+        assert len(k) > 2 * nf
+    if kind == "dot_lattice":
+        assert len(o.stage(0, 0)) > (w - 38) * (h - 38) // 6
+
+
 def test_stereo_batch_threads_agree_with_oracle_counts():
     left, right = gen_synth.frame_batch(6, 376, 1241, 50, stereo=True)
     params = (2000, 1.2, 8, 20, 7)

@@ -227,11 +227,9 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
         // score = max(margin, minTh) - minTh: 0 when the pixel is not a corner at minTh
         const unsigned sA = score_of_ring(dP, c.x, k1);
         const unsigned sB = score_of_ring(dQ, c.y, k1);
+        // (the up to 3 + 3 pixels of the first / last group outside the tile's detection columns are scored and queued like
+        // the rest: NMS never reads them as neighbours — the cell test masks those columns — and drops their own entries)
         packed = __byte_perm(sA, sB, 0x6420u);
-        // pixels of the first / last group outside the tile's detection columns
-        const int lo = offL - 4 * g, hi = offL + TW - 4 * g;
-        if (lo > 0) packed &= 0xffffffffu << (8 * lo);
-        if (hi < 4) packed &= 0xffffffffu >> (8 * (4 - hi));
         *reinterpret_cast<unsigned *>(sScore + y * sp + 4 * g) = packed;
       }
       // queue the non-zero scores as (row << 8 | score column); one shared-memory reservation per lane that has any
@@ -258,6 +256,7 @@ k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict_
     const uint8_t *c0 = sScore + y * sp + sx;
     const int s = c0[0];
     const int x = sx - offL;                               // tile coordinate
+    if (x < 0 || x >= TW) continue;                        // group overhang next to the tile
     const int c = (x >= G.wCell) + (x >= 2 * G.wCell) + (x >= 3 * G.wCell);
     const int cx0 = c * G.wCell, cx1 = min(cx0 + G.wCell, TW);
     // neighbours outside the cell's rectangle count as 0: rows -1 / TH are the zero halo, columns are masked

@@ -56,6 +56,33 @@ def test_reference_compute_stereo_matches_equals_oracle(w, h, nf, seed, cam):
     assert np.array_equal(ru, ou) and np.array_equal(rz, oz)
 
 
+def test_reference_compute_stereo_matches_equals_oracle_on_adversarial_pairs():
+    """The pairs of tests/test_gpu_stereo.py::test_stereo_edge_cases_in_one_batch through the reference's own Frame.cc:
+    no right keypoints, no left keypoints, a 2-px dot lattice shifted by 6 px, 0 / 255 noise shifted by 10 px."""
+    h, w = 263, 341
+    lat = np.zeros((h, w + 6), np.uint8)
+    ii, jj = np.meshgrid(np.arange(0, w + 6, 2) // 2, np.arange(0, h, 2) // 2)
+    lat[::2, ::2] = (50 + (ii * 24 + jj) % 192).astype(np.uint8)
+    noise = (np.random.default_rng(4).integers(0, 2, (h, w + 10)) * 255).astype(np.uint8)
+    tex, flat = gen_synth.texture(h, w, 3), np.full((h, w), 90, np.uint8)
+    pairs = [(tex, flat), (flat, tex), (lat[:, :-6], lat[:, 6:]), (noise[:, :-10], noise[:, 10:])]
+    params = (500, 1.2, 8, 20, 7)
+    mbf = 386.1448
+    mb = np.float32(np.float32(mbf) / np.float32(718.856))
+    lib = slam_ref.SlamLib("ref")
+    for i, (l, r) in enumerate(pairs):
+        l, r = np.ascontiguousarray(l), np.ascontiguousarray(r)
+        ol, orr = oracle.OracleExtractor(*params), oracle.OracleExtractor(*params)
+        (kl, dl), (kr, dr) = ol(l), orr(r)
+        ou, oz, _, kept = oracle.stereo(ol, orr, kl, dl, kr, dr, mbf, mb)
+        if len(kl) == 0:
+            assert len(ou) == 0
+            continue
+        ru, rz, matched = lib.compute_stereo(params, l, r, kl, dl, kr, dr, mbf, float(mb))
+        assert np.array_equal(ru, ou) and np.array_equal(rz, oz), i
+        assert matched == kept and (matched == 0) == (i == 0)
+
+
 def test_descriptor_distance_is_the_reference_popcount():
     rng = np.random.default_rng(0)
     a = rng.integers(0, 256, (500, 32), dtype=np.uint8)

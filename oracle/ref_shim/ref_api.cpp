@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <new>
 #include <thread>
 #include <vector>
@@ -25,9 +26,12 @@ extern "C" int orb_oracle_stereo_views(int nlevels, const uint8_t *const *planes
 
 namespace {
 constexpr size_t kSlab = (size_t)2 << 30;          // one arena: 2 GiB of address space, committed on touch
-constexpr size_t kReserve = (size_t)2 << 40;       // 2 TiB reservation = 1024 slabs = 512 extractor handles
+constexpr size_t kReserve = (size_t)2 << 40;       // 2 TiB reservation = 1024 slabs = 512 extractor handles ALIVE at once
 char *g_base = nullptr;
-std::atomic<size_t> g_slabs{0};
+size_t g_slabs = 0;                                // slabs ever carved out of the reservation (guarded by g_slabMutex)
+size_t g_freeSlab[kReserve / kSlab];               // slabs handed back by destroyed handles, reused before new ones are carved
+size_t g_nFree = 0;                                // (a plain array: this file replaces operator new, so no std::vector here)
+std::mutex g_slabMutex;
 std::atomic<int> g_init{0};
 
 void reserve_once() {
@@ -50,17 +54,37 @@ struct Arena {
     reserve_once();
     cur ^= 1;
     if (!slab[cur]) {
-      const size_t i = g_slabs.fetch_add(1);
-      if ((i + 1) * kSlab > kReserve) { fprintf(stderr, "ref arena: out of slabs\n"); abort(); }
+      std::lock_guard<std::mutex> lock(g_slabMutex);
+      size_t i;
+      if (g_nFree) {
+        i = g_freeSlab[--g_nFree];
+      } else {
+        i = g_slabs++;
+        if ((i + 1) * kSlab > kReserve) { fprintf(stderr, "ref arena: out of slabs (more than %zu arenas alive)\n", kReserve / kSlab); abort(); }
+      }
       slab[cur] = g_base + i * kSlab;
     }
     used = 0;
   }
+  // A handle's slabs go back to the free list when it dies; the pages it touched are dropped so that a process that
+  // creates and destroys handles for hours (bench.py's reference arm: two per worker thread per call) stays bounded in
+  // both address space and resident memory.  Objects still pointing into the slab (the extractor's pyramid Mats, destroyed
+  // after the arena) are only ever passed to release(), which ignores arena addresses.
+  ~Arena() {
+    for (int k = 0; k < 2; k++) {
+      if (!slab[k]) continue;
+      madvise(slab[k], high[k] ? high[k] : 1, MADV_DONTNEED);
+      std::lock_guard<std::mutex> lock(g_slabMutex);
+      g_freeSlab[g_nFree++] = (size_t)(slab[k] - g_base) / kSlab;
+    }
+  }
+  size_t high[2] = {0, 0};                          // high-water mark per slab = what MADV_DONTNEED has to cover
   void *take(size_t n) {
     n = (n + 15) & ~(size_t)15;
     if (used + n > kSlab) { fprintf(stderr, "ref arena exhausted\n"); abort(); }
     void *p = slab[cur] + used;
     used += n;
+    if (used > high[cur]) high[cur] = used;
     return p;
   }
 };

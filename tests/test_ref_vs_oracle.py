@@ -88,3 +88,17 @@ def test_stereo_batch_threads_agree_with_oracle_counts():
     cl, cr, m = ref.stereo_batch(params, left, right, 386.1448, np.float32(386.1448) / np.float32(718.856), 3)
     ol, orr, om = oracle.stereo_batch(params, left, right, 386.1448, np.float32(np.float32(386.1448) / np.float32(718.856)), 3)
     assert np.array_equal(cl, ol) and np.array_equal(cr, orr) and np.array_equal(m, om)
+
+
+def test_stereo_batch_survives_many_calls():
+    """bench.py's reference arm calls ref.stereo_batch once per step with fresh handles per worker thread; their arenas
+    must go back to the free list (round 1: `ref arena: out of slabs` at call 17 of the driver's 25)."""
+    rng = np.random.default_rng(0)
+    left = rng.integers(0, 256, (128, 120, 160), dtype=np.uint8)
+    right = rng.integers(0, 256, (128, 120, 160), dtype=np.uint8)
+    first = None
+    for _ in range(60):           # 60 calls x 32 threads x 2 handles x 2 slabs = 7680 slab requests against 1024 reserved
+        out = ref.stereo_batch((300, 1.2, 8, 20, 7), left, right, 40.0, 0.1, 32)
+        if first is None:
+            first = out
+        assert all(np.array_equal(a, b) for a, b in zip(first, out))

@@ -8,6 +8,8 @@
 // restatement of the candidate loops is itself pinned to the reference.  The GPU tests link the same shim against the
 // real liborbgpu.so instead.
 #include <cstdint>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "../include/orbgpu.h"
@@ -41,15 +43,45 @@ int orbgpu_vocabulary_transform(orbgpu_vocabulary *h, const uint8_t *descriptors
                                   levelsup, word_ids, node_ids);
 }
 
+// Lifetime audit (what a freed device buffer would punish on the GPU, made observable on the CPU): every live set has a
+// count of searches running on it; destroying a set that is being searched, or searching one that is not alive, is a
+// violation the concurrency test of tests/test_matcher_ref.py reads back.
+static std::mutex g_liveMutex;
+static std::map<orbgpu_features *, int> g_live;
+static int g_violations = 0;
+int orbgpu_oracle_backend_violations(void) { std::lock_guard<std::mutex> l(g_liveMutex); return g_violations; }
+
 int orbgpu_features_create(const orbgpu_features_desc *desc, orbgpu_features **out) {
   *out = reinterpret_cast<orbgpu_features *>(orb_oracle_features_create(desc));
+  std::lock_guard<std::mutex> l(g_liveMutex);
+  g_live[*out] = 0;
   return ORBGPU_OK;
 }
-void orbgpu_features_destroy(orbgpu_features *f) { orb_oracle_features_destroy(reinterpret_cast<OracleFeatures *>(f)); }
+void orbgpu_features_destroy(orbgpu_features *f) {
+  {
+    std::lock_guard<std::mutex> l(g_liveMutex);
+    auto it = g_live.find(f);
+    if (it == g_live.end() || it->second != 0) g_violations++;
+    if (it != g_live.end()) g_live.erase(it);
+  }
+  orb_oracle_features_destroy(reinterpret_cast<OracleFeatures *>(f));
+}
 int orbgpu_search(orbgpu_features *f, const orbgpu_query *queries, const uint8_t *query_descriptors, int nq, const uint8_t *occupied,
                   const int32_t *cand, int ncand, const orbgpu_search_policy *policy, orbgpu_match *result, int *iterations) {
   if (iterations) *iterations = 1;
-  return orb_oracle_search(reinterpret_cast<const OracleFeatures *>(f), queries, query_descriptors, nq, occupied, cand, ncand, policy, result);
+  {
+    std::lock_guard<std::mutex> l(g_liveMutex);
+    auto it = g_live.find(f);
+    if (it == g_live.end()) { g_violations++; return ORBGPU_E_INVALID; }
+    it->second++;
+  }
+  const int rc = orb_oracle_search(reinterpret_cast<const OracleFeatures *>(f), queries, query_descriptors, nq, occupied, cand, ncand, policy, result);
+  {
+    std::lock_guard<std::mutex> l(g_liveMutex);
+    auto it = g_live.find(f);
+    if (it == g_live.end()) g_violations++; else it->second--;
+  }
+  return rc;
 }
 const char *orbgpu_last_error(void) { return "oracle backend"; }
 }

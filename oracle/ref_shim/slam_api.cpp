@@ -256,6 +256,28 @@ int slam_search_sim3_projection(void *h, int kf, const float *Scw, const int *mp
   for (int i = 0; i < K->N; i++) matched[i] = S->idOf(m[i]);
   return r;
 }
+// Concurrency stress for the drop-in's feature-set cache: `nthreads` host threads (std::thread, no interpreter lock in the way)
+// run SearchByProjection(KF, Scw, ...) over ALL keyframes `rounds` times, thread t starting at keyframe t * nkf / nthreads.
+// counts[t * nkf + k] = matches thread t found in keyframe k in its last round (all threads must agree).
+void slam_stress_sim3_projection(void *h, const float *Scws, const int *mps, int n, int th, float nnratio, int nthreads, int rounds, int *counts) {
+  Scene *S = (Scene *)h;
+  const int nkf = (int)S->kfs.size();
+  std::vector<MapPoint *> pts;
+  for (int i = 0; i < n; i++) pts.push_back(S->mps[mps[i]]);
+  auto worker = [&](int t) {
+    for (int r = 0; r < rounds; r++)
+      for (int j = 0; j < nkf; j++) {
+        const int k = (j + t * nkf / nthreads) % nkf;
+        KeyFrame *K = S->kfs[k];
+        std::vector<MapPoint *> m(K->N, static_cast<MapPoint *>(NULL));
+        ORBmatcher matcher(nnratio, true);
+        counts[t * nkf + k] = matcher.SearchByProjection(K, mat_from(Scws + 16 * k, 4, 4), pts, m, th);
+      }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nthreads; t++) pool.emplace_back(worker, t);
+  for (auto &t : pool) t.join();
+}
 int slam_search_bow_frame(void *h, int kf, int f, int *out, float nnratio, int checkOri) {
   Scene *S = (Scene *)h;
   std::vector<MapPoint *> m;

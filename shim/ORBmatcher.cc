@@ -23,7 +23,9 @@
 #include <cmath>
 #include <cstring>
 #include <list>
+#include <iterator>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -42,27 +44,43 @@ const int ORBmatcher::HISTO_LENGTH = 30;
 namespace {
 
 // ---- device-resident feature sets ---------------------------------------------------------------------------------
+// Tracking, LocalMapping and LoopClosing call into this file concurrently.  Cache entries are therefore SHARED: a search
+// holds a reference to its feature set for the whole device call, and an entry evicted meanwhile by another thread is only
+// destroyed when its last user lets go.  (The set itself is read-only after creation; every thread searches through its own
+// thread-local workspace and stream inside liborbgpu.)
+using FeatureSet = std::shared_ptr<orbgpu_features>;
 struct CacheEntry {
   int kind; unsigned long id; int n; uint64_t digest;
-  orbgpu_features *set;
+  FeatureSet set;
 };
 std::mutex g_cacheMutex;
 std::list<CacheEntry> g_cache;                 // most recently used first
-constexpr size_t kCacheEntries = 48;
+size_t g_cacheEntries = 48;                   // orbgpu_shim_set_feature_cache_capacity
 
-uint64_t sample_digest(const vector<cv::KeyPoint> &keys, const cv::Mat &desc, const vector<float> &uRight) {
-  uint64_t h = 1469598103934665603ull;
+// Digest of EVERYTHING the device copy is built from (every keypoint record, descriptor row and uRight, 64 bits at a time:
+// ~140 KB per frame, microseconds): Frame::nNextId restarts at 0 on Tracking::Reset, so (id, n) alone would alias a stale set.
+uint64_t content_digest(const vector<cv::KeyPoint> &keys, const cv::Mat &desc, const vector<float> &uRight, const float *geometry, int ngeo) {
+  uint64_t h = 0x9e3779b97f4a7c15ull;
   auto mix = [&](const void *p, size_t nbytes) {
     const unsigned char *b = (const unsigned char *)p;
-    for (size_t i = 0; i < nbytes; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    size_t i = 0;
+    for (; i + 8 <= nbytes; i += 8) {
+      uint64_t w;
+      std::memcpy(&w, b + i, 8);
+      h = (h ^ w) * 0xff51afd7ed558ccdull;
+      h ^= h >> 29;
+    }
+    uint64_t tail = nbytes - i;
+    for (; i < nbytes; i++) tail = (tail << 8) | b[i];
+    h = (h ^ tail) * 0xc4ceb9fe1a85ec53ull;
+    h ^= h >> 32;
   };
   const int n = (int)keys.size();
-  const int stride = n > 64 ? n / 64 : 1;
-  for (int i = 0; i < n; i += stride) {
-    mix(&keys[i].pt, sizeof(keys[i].pt));
-    mix(desc.ptr(i), 32);
-    if (!uRight.empty()) mix(&uRight[i], 4);
-  }
+  if (n) mix(keys.data(), (size_t)n * sizeof(cv::KeyPoint));
+  if (desc.isContinuous()) { if (n) mix(desc.ptr(0), (size_t)n * 32); }
+  else for (int i = 0; i < n; i++) mix(desc.ptr(i), 32);
+  if (!uRight.empty()) mix(uRight.data(), uRight.size() * sizeof(float));
+  mix(geometry, (size_t)ngeo * sizeof(float));
   return h;
 }
 
@@ -70,17 +88,22 @@ uint64_t sample_digest(const vector<cv::KeyPoint> &keys, const cv::Mat &desc, co
   throw std::runtime_error(std::string("orbgpu ORBmatcher: ") + what + ": " + orbgpu_last_error());
 }
 
-orbgpu_features *resident(int kind, unsigned long id, const vector<cv::KeyPoint> &keysUn, const vector<float> &uRight,
-                          const cv::Mat &desc, float minX, float minY, float wInv, float hInv, int cols, int rows, float qMinX,
-                          float qMinY) {
+FeatureSet resident(int kind, unsigned long id, const vector<cv::KeyPoint> &keysUn, const vector<float> &uRight,
+                    const cv::Mat &desc, float minX, float minY, float wInv, float hInv, int cols, int rows, float qMinX,
+                    float qMinY) {
   const int n = (int)keysUn.size();
-  const uint64_t digest = sample_digest(keysUn, desc, uRight);
-  std::lock_guard<std::mutex> lock(g_cacheMutex);
-  for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
-    if (it->kind == kind && it->id == id && it->n == n && it->digest == digest) {
-      g_cache.splice(g_cache.begin(), g_cache, it);
-      return g_cache.front().set;
-    }
+  const float geometry[8] = {minX, minY, wInv, hInv, (float)cols, (float)rows, qMinX, qMinY};
+  const uint64_t digest = content_digest(keysUn, desc, uRight, geometry, 8);
+  {
+    std::lock_guard<std::mutex> lock(g_cacheMutex);
+    for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
+      if (it->kind == kind && it->id == id && it->n == n && it->digest == digest) {
+        g_cache.splice(g_cache.begin(), g_cache, it);
+        return g_cache.front().set;
+      }
+  }
+  // upload outside the lock (a device call): two threads that miss on the same frame at once both build a set, the second
+  // insert simply shadows the first, whose users keep it alive until they are done
   static_assert(sizeof(cv::KeyPoint) == sizeof(orbgpu_keypoint), "cv::KeyPoint must be the 28-byte record of orbgpu.h");
   vector<unsigned char> rows32((size_t)n * 32);
   for (int i = 0; i < n; i++) std::memcpy(&rows32[(size_t)i * 32], desc.ptr(i), 32);
@@ -91,20 +114,25 @@ orbgpu_features *resident(int kind, unsigned long id, const vector<cv::KeyPoint>
   d.descriptors = rows32.data();
   d.min_x = minX; d.min_y = minY; d.grid_w_inv = wInv; d.grid_h_inv = hInv; d.grid_cols = cols; d.grid_rows = rows;
   d.query_min_x = qMinX; d.query_min_y = qMinY; d.device = -1;
-  orbgpu_features *set = nullptr;
-  if (orbgpu_features_create(&d, &set) != ORBGPU_OK) fail("orbgpu_features_create");
-  g_cache.push_front(CacheEntry{kind, id, n, digest, set});
-  while (g_cache.size() > kCacheEntries) { orbgpu_features_destroy(g_cache.back().set); g_cache.pop_back(); }
+  orbgpu_features *raw = nullptr;
+  if (orbgpu_features_create(&d, &raw) != ORBGPU_OK) fail("orbgpu_features_create");
+  FeatureSet set(raw, orbgpu_features_destroy);
+  std::list<CacheEntry> evicted;               // destroyed (if unused) after the lock is released
+  {
+    std::lock_guard<std::mutex> lock(g_cacheMutex);
+    g_cache.push_front(CacheEntry{kind, id, n, digest, set});
+    while (g_cache.size() > g_cacheEntries) evicted.splice(evicted.begin(), g_cache, std::prev(g_cache.end()));
+  }
   return set;
 }
 
-orbgpu_features *resident(const Frame &F) {
+FeatureSet resident(const Frame &F) {
   return resident(0, F.mnId, F.mvKeysUn, F.mvuRight, F.mDescriptors, Frame::mnMinX, Frame::mnMinY, Frame::mfGridElementWidthInv,
                   Frame::mfGridElementHeightInv, FRAME_GRID_COLS, FRAME_GRID_ROWS, Frame::mnMinX, Frame::mnMinY);
 }
 // A KeyFrame's grid is a copy of its Frame's (KeyFrame.cc:56-61) — built with the Frame's float bounds — but its
 // window walk reads the truncated integer bounds of KeyFrame.h:190-193.
-orbgpu_features *resident(const KeyFrame *K) {
+FeatureSet resident(const KeyFrame *K) {
   return resident(1, K->mnId, K->mvKeysUn, K->mvuRight, K->mDescriptors, Frame::mnMinX, Frame::mnMinY, K->mfGridElementWidthInv,
                   K->mfGridElementHeightInv, K->mnGridCols, K->mnGridRows, (float)K->mnMinX, (float)K->mnMinY);
 }
@@ -123,10 +151,11 @@ struct Batch {
     std::memcpy(&desc[o], descriptor.ptr(0), 32);
     tag.push_back(t);
   }
-  void run(orbgpu_features *set, const orbgpu_search_policy &P, const vector<unsigned char> *occupied) {
+  // `set` is held by value: the device copy outlives the call even if another thread evicts it from the cache meanwhile
+  void run(FeatureSet set, const orbgpu_search_policy &P, const vector<unsigned char> *occupied) {
     out.resize(q.size());
     if (q.empty()) return;
-    if (orbgpu_search(set, q.data(), desc.data(), (int)q.size(), occupied ? occupied->data() : nullptr, cand.data(), (int)cand.size(),
+    if (orbgpu_search(set.get(), q.data(), desc.data(), (int)q.size(), occupied ? occupied->data() : nullptr, cand.data(), (int)cand.size(),
                       &P, out.data(), nullptr) != ORBGPU_OK)
       fail("orbgpu_search");
   }
@@ -218,10 +247,18 @@ void copy_levels(float *dst, const vector<float> &src) {
 
 }  // namespace
 
-extern "C" void orbgpu_shim_clear_feature_cache() {
+// How many Frame / KeyFrame feature sets stay resident on the device (~70 B per keypoint each); at least 1.
+extern "C" void orbgpu_shim_set_feature_cache_capacity(int entries) {
+  std::list<CacheEntry> dropped;
   std::lock_guard<std::mutex> lock(g_cacheMutex);
-  for (auto &e : g_cache) orbgpu_features_destroy(e.set);
-  g_cache.clear();
+  g_cacheEntries = (size_t)(entries < 1 ? 1 : entries);
+  while (g_cache.size() > g_cacheEntries) dropped.splice(dropped.begin(), g_cache, std::prev(g_cache.end()));
+}
+
+extern "C" void orbgpu_shim_clear_feature_cache() {
+  std::list<CacheEntry> dropped;               // sets still in use by a running search die with their last user
+  std::lock_guard<std::mutex> lock(g_cacheMutex);
+  dropped.swap(g_cache);
 }
 
 ORBmatcher::ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}

@@ -131,3 +131,38 @@ def test_reference_compute_distinctive_descriptors_equals_oracle():
     for g in range(S.n_mps):
         assert np.array_equal(rows[offsets[g] + idx[g]], chosen[g]), g
     S.close()
+
+
+def test_shim_feature_cache_is_safe_under_concurrent_eviction():
+    """Tracking, LocalMapping and LoopClosing call the drop-in ORBmatcher at the same time.  Four host threads search 60
+    keyframes with a cache of two device sets, each starting at another keyframe: every search must see its own feature
+    set alive for the whole call although the other threads keep evicting it (round 1 returned a raw pointer into the
+    cache).  The test backend audits lifetimes: a set destroyed under a running search, or searched after its death, counts."""
+    lib = slam_ref.SlamLib("shim_cpu")
+    W = slam_ref.World(23, npoints=260, clutter=40)
+    S = slam_ref.Scene(lib, W)
+    views, kfs, poses = [], [], []
+    for i in range(60):
+        T = slam_ref._pose(0.001 * i, -0.004 * i, 0.0, [-0.05 * i, 0.0, -0.03 * i])
+        V = W.observe(T)
+        kfs.append(S.add_keyframe(S.add_frame(V)))
+        views.append(V)
+        poses.append(np.asarray(T, np.float32))
+    S.add_mappoints({p: o for p, o in slam_ref.observations_from_views(views[:6]).items()})
+    mps = np.arange(S.n_mps, dtype=np.int32)
+    Scws = np.ascontiguousarray(np.stack(poses), np.float32)
+    import ctypes
+    lib.L.slam_stress_sim3_projection.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.L.slam_stress_sim3_projection.restype = None
+    lib.L.orbgpu_oracle_backend_violations.restype = ctypes.c_int
+    want = np.zeros((1, 60), np.int32)
+    lib.L.slam_stress_sim3_projection(S.h, slam_ref._ptr(Scws), slam_ref._ptr(mps), len(mps), 10, 0.75, 1, 1, slam_ref._ptr(want))
+    assert want.sum() > 500
+    lib.L.orbgpu_shim_set_feature_cache_capacity(2)          # every search evicts: the hazard no longer needs a long search to show
+    got = np.zeros((4, 60), np.int32)
+    lib.L.slam_stress_sim3_projection(S.h, slam_ref._ptr(Scws), slam_ref._ptr(mps), len(mps), 10, 0.75, 4, 8, slam_ref._ptr(got))
+    S.close()
+    assert np.array_equal(got, np.repeat(want, 4, axis=0))
+    lib.L.orbgpu_shim_clear_feature_cache()
+    lib.L.orbgpu_shim_set_feature_cache_capacity(48)
+    assert lib.L.orbgpu_oracle_backend_violations() == 0

@@ -97,7 +97,9 @@ int orbgpu_extract_batch(orbgpu_extractor *e, const uint8_t *images, int count, 
  * (refactored_orb_slam2_b200/pipeline.py): _async enqueues the chunked H2D copies, the kernels and the D2H copies and
  * returns; orbgpu_wait blocks until everything queued on the handle (including an orbgpu_stereo_match_async) has
  * landed in the host buffers, then reports device-side overflow and counts[i] > capacity.  Host buffers should be
- * pinned, and must stay valid until orbgpu_wait returns.  orbgpu_extract_batch == _async + orbgpu_wait. */
+ * pinned, and must stay valid until orbgpu_wait returns.  orbgpu_extract_batch == _async + orbgpu_wait.
+ * ONE batch per handle: a second _async (or orbgpu_extract_batch_device) before orbgpu_wait returns ORBGPU_E_INVALID —
+ * its kernels would overwrite the device results under the first batch's D2H copies. */
 int orbgpu_extract_batch_async(orbgpu_extractor *e, const uint8_t *images, int count, int width, int height,
                                size_t row_step, size_t image_step, orbgpu_keypoint *keypoints,
                                uint8_t *descriptors, int capacity, int32_t *counts);

@@ -98,7 +98,10 @@ struct orbgpu_extractor {
     cudaGraphExec_t exec = nullptr;
     const uint8_t *dImages = nullptr; int imgBase = -1, batch = 0, w = 0, h = 0; size_t rowStep = 0, imgStep = 0;
     int launches = 0;
-  } graph;
+  };
+  static constexpr int kGraphSlots = 4;      // a 16-image host batch is two graphed chunks: one slot per (input, first image, count) key
+  ExtractGraph graphs[kGraphSlots];
+  int graphVictim = 0;
   // outputs of an enqueued, not yet awaited host-buffer batch (orbgpu_extract_batch_async .. orbgpu_wait)
   const int32_t *pendingCounts = nullptr; int pendingCount = 0, pendingCapacity = 0;
   // host-buffer pipeline: copy streams + per-chunk events
@@ -382,9 +385,16 @@ constexpr int kGraphMaxBatch = 8;
 int run_extract_range_graphed(orbgpu_extractor *e, const uint8_t *dImages, int imgBase, int batch, size_t rowStep, size_t imgStep) {
   static const bool disabled = getenv("ORBGPU_NO_GRAPH") != nullptr;
   if (disabled || e->profiling || batch > kGraphMaxBatch) return run_extract_range(e, dImages, imgBase, batch, rowStep, imgStep);
-  orbgpu_extractor::ExtractGraph &G = e->graph;
-  const bool hit = G.exec && G.dImages == dImages && G.imgBase == imgBase && G.batch == batch && G.w == e->cfgW && G.h == e->cfgH &&
-                   G.rowStep == rowStep && G.imgStep == imgStep;
+  orbgpu_extractor::ExtractGraph *slot = nullptr;
+  for (auto &g : e->graphs)
+    if (g.exec && g.dImages == dImages && g.imgBase == imgBase && g.batch == batch && g.w == e->cfgW && g.h == e->cfgH && g.rowStep == rowStep &&
+        g.imgStep == imgStep) { slot = &g; break; }
+  const bool hit = slot != nullptr;
+  if (!hit) {
+    for (auto &g : e->graphs) if (!g.exec) { slot = &g; break; }
+    if (!slot) { slot = &e->graphs[e->graphVictim]; e->graphVictim = (e->graphVictim + 1) % orbgpu_extractor::kGraphSlots; }
+  }
+  orbgpu_extractor::ExtractGraph &G = *slot;
   if (!hit) {
     if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
     const long long before = g_launches;
@@ -516,6 +526,8 @@ int orbgpu_extractor_create(const orbgpu_extractor_params *params, orbgpu_extrac
   ORBGPU_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   ORBGPU_CUDA_CHECK(cudaEventCreateWithFlags(&e->evDone, cudaEventDisableTiming));
   ORBGPU_CUDA_CHECK(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+  ORBGPU_CUDA_CHECK(describe_prepare());
+  ORBGPU_CUDA_CHECK(describe_prepare_lat());
   ORBGPU_CUDA_CHECK(cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming));
   ORBGPU_CUDA_CHECK(cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming));
   LevelTable T;
@@ -554,7 +566,7 @@ void orbgpu_extractor_destroy(orbgpu_extractor *e) {
   void *ptrs[] = {e->dT, e->dTabs, e->dTiles, e->dBlurTiles, e->dRzTiles, e->dInput, e->dPyr, e->dBlur, e->dCand, e->dNodeOf, e->dSel, e->dCandCount,
                   e->dSelCount, e->dKpCount, e->dKps, e->dDesc, e->dStatus, e->dURight, e->dDepth, e->dBestSad, e->dRowStart, e->dSorted};
   for (void *q : ptrs) if (q) cudaFree(q);
-  if (e->graph.exec) cudaGraphExecDestroy(e->graph.exec);
+  for (auto &g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (e->evDone) cudaEventDestroy(e->evDone);
   if (e->evFork) cudaEventDestroy(e->evFork);
   if (e->evJoin) cudaEventDestroy(e->evJoin);
@@ -627,6 +639,7 @@ int orbgpu_extract_batch_device(orbgpu_extractor *e, const uint8_t *d_images, in
   if (!e || !d_images) { set_error("null argument"); return ORBGPU_E_INVALID; }
   if (count < 1 || count > e->p.max_batch) { set_error("batch %d outside 1..%d", count, e->p.max_batch); return ORBGPU_E_CAPACITY; }
   if (width < 1 || height < 1 || row_step < (size_t)width) { set_error("bad image shape"); return ORBGPU_E_INVALID; }
+  if (e->pendingCounts) { set_error("a batch enqueued with orbgpu_extract_batch_async has not been awaited (orbgpu_wait)"); return ORBGPU_E_INVALID; }
   DeviceGuard guard(e->device);
   return run_extract(e, d_images, count, width, height, row_step, image_step);
 }
@@ -685,6 +698,9 @@ static int enqueue_extract_batch(orbgpu_extractor *e, const uint8_t *images, int
     return ORBGPU_E_CAPACITY;
   }
   if (capacity < 1 || ((keypoints == nullptr) != (descriptors == nullptr))) { set_error("bad output buffers"); return ORBGPU_E_INVALID; }
+  // one host-buffer batch per handle: the next batch's kernels would overwrite dKps / dDesc / dKpCount under the previous
+  // batch's D2H copies, which run on their own stream
+  if (e->pendingCounts) { set_error("a batch enqueued with orbgpu_extract_batch_async has not been awaited (orbgpu_wait)"); return ORBGPU_E_INVALID; }
   DeviceGuard guard(e->device);
   int rc = configure(e, width, height);
   if (rc) return rc;
@@ -857,8 +873,9 @@ int orbgpu_stereo_match_device(orbgpu_extractor *L, orbgpu_extractor *R, int fir
     return ORBGPU_E_INVALID;
   }
   if (L->cfgW != R->cfgW || L->cfgH != R->cfgH || L->p.nlevels != R->p.nlevels || L->p.scale_factor != R->p.scale_factor ||
-      L->p.max_batch != R->p.max_batch || L->p.max_width != R->p.max_width || L->p.max_height != R->p.max_height) {
-    set_error("left and right extractors must share image size, pyramid parameters and buffer sizing");
+      L->p.max_batch != R->p.max_batch || L->p.max_width != R->p.max_width || L->p.max_height != R->p.max_height ||
+      L->p.nfeatures != R->p.nfeatures || L->kpCap != R->kpCap) {      // dSorted / row buckets are sized by the LEFT handle's kpCap
+    set_error("left and right extractors must share image size, pyramid parameters, nfeatures and buffer sizing");
     return ORBGPU_E_INVALID;
   }
   if (!(mb > 0.f) || !(mbf > 0.f)) { set_error("mbf and mb must be positive"); return ORBGPU_E_INVALID; }

@@ -229,21 +229,25 @@ k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, co
 
 }  // namespace
 
-cudaError_t VNAME(launch_describe)(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, cudaStream_t s) {
+// Fills this variant's d_patternT on the current device.  Called from orbgpu_extractor_create — outside any stream capture
+// (small batches replay a captured graph, and a synchronize inside the capture would invalidate it) — and complete on
+// return, so every stream that launches k_describe afterwards sees the table.
+cudaError_t VNAME(describe_prepare)() {
   static std::mutex mu;
   static bool ready[64] = {};
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    std::lock_guard<std::mutex> lock(mu);
-    if (!ready[dev & 63]) {
-      k_init_pattern<<<2, 256, 0, s>>>();
-      cudaError_t e = cudaGetLastError();
-      if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // once per device: other handles' streams must see the table
-      if (e != cudaSuccess) return e;
-      ready[dev & 63] = true;
-    }
-  }
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  if (ready[dev & 63]) return cudaSuccess;
+  k_init_pattern<<<2, 256>>>();
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) ready[dev & 63] = true;
+  return e;
+}
+
+cudaError_t VNAME(launch_describe)(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, cudaStream_t s) {
   dim3 grid((T.kpCap + kWarpsPerCta - 1) / kWarpsPerCta, batch);
   k_describe<<<grid, kWarpsPerCta * 32, 0, s>>>(B.dT, B.pyr, B.blur, B.sel, B.selCount, B.kps, B.desc, B.kpCount,
                                                 B.status, imgBase);

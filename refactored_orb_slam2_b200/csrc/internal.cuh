@@ -136,6 +136,8 @@ cudaError_t launch_octree(const LevelTable &T, const ExtractBuffers &B, int imgB
                           cudaStream_t s);
 int hamming_dense_q(int nq);
 cudaError_t launch_describe(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, cudaStream_t s);
+cudaError_t describe_prepare();       // pattern table of the variant, once per device, outside stream capture
+cudaError_t describe_prepare_lat();
 // second thread shape of octree / describe / stereo for small batches (octree_lat.cu, describe_lat.cu, stereo_lat.cu)
 constexpr int kLatencyBatch = 16;
 cudaError_t launch_octree_lat(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, int smemBytes, cudaStream_t s);

@@ -212,3 +212,41 @@ def test_golden_fixture(pkg):
     assert np.array_equal(gd, z["descriptors"])
     for f in gk.dtype.names:
         assert np.array_equal(gk[f], z["keypoints"][f]), f
+
+
+def test_two_graphed_chunks_and_repeat_calls(pkg):
+    """A 16-image host batch is two chunks of 8, both on the captured-graph path (one graph slot per chunk, first call on a
+    fresh handle: the descriptor pattern table must already be on the device, outside the capture).  Repeated calls replay."""
+    import ctypes as C
+    imgs = gen_synth.frame_batch(16, 240, 416, 9)
+    params = (500, 1.2, 8, 20, 7)
+    g = pkg.ORBextractor(*params, max_width=416, max_height=240, max_batch=16)
+    o = oracle.OracleExtractor(*params)
+    want = [o(imgs[i]) for i in range(16)]
+    for _ in range(3):
+        kps, desc, counts = g.extract_batch(imgs)
+        for i in range(16):
+            assert counts[i] == len(want[i][0]), i
+            assert_same_keypoints(kps[i, :counts[i]], desc[i, :counts[i]], *want[i])
+    assert pkg.lib().orbgpu_last_error() in (b"", None) or b"capture" not in pkg.lib().orbgpu_last_error()
+
+
+def test_one_pending_batch_per_handle(pkg):
+    """A second _async (or a device-resident extraction) before orbgpu_wait would overwrite results under the first batch's
+    D2H copies: it is rejected, and the handle works again after the wait."""
+    import ctypes as C
+    from refactored_orb_slam2_b200._lib import KP_DTYPE, E_INVALID, ptr
+    imgs = gen_synth.frame_batch(4, 240, 416, 3)
+    params = (500, 1.2, 8, 20, 7)
+    g = pkg.ORBextractor(*params, max_width=416, max_height=240, max_batch=4)
+    cap = g.capacity
+    kps, desc, counts = np.empty((4, cap), KP_DTYPE), np.empty((4, cap, 32), np.uint8), np.zeros(4, np.int32)
+    L = pkg.lib()
+    args = (g.handle, ptr(imgs), 4, 416, 240, 416, 240 * 416, ptr(kps), ptr(desc), cap, ptr(counts))
+    assert L.orbgpu_extract_batch_async(*args) == 0
+    assert L.orbgpu_extract_batch_async(*args) == E_INVALID
+    assert L.orbgpu_extract_batch_device(g.handle, ptr(imgs), 4, 416, 240, 416, 240 * 416) == E_INVALID
+    assert L.orbgpu_wait(g.handle) == 0
+    ok, od = oracle.OracleExtractor(*params)(imgs[2])
+    assert_same_keypoints(kps[2, :counts[2]], desc[2, :counts[2]], ok, od)
+    assert L.orbgpu_extract_batch_async(*args) == 0 and L.orbgpu_wait(g.handle) == 0

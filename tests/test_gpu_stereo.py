@@ -130,3 +130,18 @@ def test_pipeline_equals_sequential_calls(pkg):
             assert np.array_equal(k[i, :c[i]]["angle"], k2[i, :c2[i]]["angle"])
         for i in range(npairs):
             assert np.array_equal(u[i, :c[i]], u2[i, :c2[i]]) and np.array_equal(z[i, :c[i]], z2[i, :c2[i]])
+
+
+def test_left_and_right_handles_must_share_nfeatures(pkg):
+    """The row buckets are sized by the left handle's keypoint capacity: a right extractor with more features is rejected
+    instead of writing past them."""
+    from refactored_orb_slam2_b200._lib import OrbGpuError
+    h, w = 240, 416
+    left, right = gen_synth.stereo_pair(h, w, 5)
+    gl = pkg.ORBextractor(300, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=1)
+    gr = pkg.ORBextractor(900, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=1)
+    gl.extract_batch(left[None])
+    gr.extract_batch(right[None])
+    bf, fx = KITTI
+    with pytest.raises(OrbGpuError):
+        pkg.ComputeStereoMatches(gl, gr, bf, np.float32(bf) / np.float32(fx), first_left=0, first_right=0, pairs=1)

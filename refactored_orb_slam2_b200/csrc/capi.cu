@@ -70,7 +70,7 @@ struct orbgpu_extractor {
   int2 *dTabs = nullptr; size_t tabsCap = 0;
   int4 *dTiles = nullptr; size_t tilesCap = 0; int ntiles = 0;
   FastConfig fastCfg{};
-  TmaMaps fastMaps{}, blurMaps{}, rzMaps{};
+  TmaMaps blurMaps{}, rzMaps{};
   int4 *dRzTiles = nullptr; size_t rzTilesCap = 0; int rzTileOff[kMaxLevels] = {}, rzTileCnt[kMaxLevels] = {};
   int rzSlotBytes = 0;
   int4 *dBlurTiles = nullptr; size_t blurTilesCap = 0; int nBlurTiles = 0;
@@ -187,8 +187,6 @@ int build_table(const orbgpu_extractor &e, int w, int h, int batchCap, LevelTabl
     selOff += (size_t)G.selCap * batchCap;
     G.scale = e.scale[l]; G.invScale = e.invScale[l];
     G.patchSize = (int)(kPatchSize * e.scale[l]);                     // ORBextractor.cc:800
-    G.fastBoxW = (int)round_up(12 + 4 + kFastCellsPerTile * G.wCell + 3 + 8, 16);   // lead + left word + tile + overhang + right words
-    G.fastBoxH = G.hCell + 6;
     if (l > 0) {
       resize_box(T, l, &G.rzBoxW, &G.rzBoxH);
       if (G.rzBoxW > 256 || G.rzBoxH > 256) G.rzBoxW = G.rzBoxH = 0;   // large scale factors: generic kernel
@@ -202,9 +200,10 @@ int build_table(const orbgpu_extractor &e, int w, int h, int batchCap, LevelTabl
     }
     for (int ci = 0; ci < G.nRows; ci++) {
       if (kEdge + ci * G.hCell >= G.h - kEdge) continue;               // empty detection rows
-      for (int cj = 0; cj < G.nCols; cj += kFastCellsPerTile) {
+      const int per = fast_cells_per_strip(G.wCell);                   // FAST strips: <= 128 pixels of whole cells, one warp each
+      for (int cj = 0; cj < G.nCols; cj += per) {
         if (kEdge + cj * G.wCell >= G.w - kEdge) continue;
-        tiles.push_back(make_int4(l, ci, cj, std::min(kFastCellsPerTile, G.nCols - cj)));
+        tiles.push_back(make_int4(l, ci, cj, std::min(per, G.nCols - cj)));
       }
     }
   }
@@ -236,17 +235,11 @@ int configure(orbgpu_extractor *e, int w, int h) {
     set_error("nfeatures too large for the shared-memory octree (%d nodes, %d bytes)", maxNodes, octSmem);
     return ORBGPU_E_UNSUPPORTED;
   }
-  if (fc.scorePitch > 256) {
-    set_error("internal: FAST tile of %d columns does not fit the 8-bit queue coordinates", fc.scorePitch);
-    return ORBGPU_E_UNSUPPORTED;
-  }
-  TmaMaps fastMaps;
-  for (int l = 0; l < T.nlevels; l++) {
-    const LevelGeom &G = T.lv[l];
-    if (G.fastBoxW > 256 || G.fastBoxH > 256) { set_error("internal: FAST TMA box %dx%d too large", G.fastBoxW, G.fastBoxH); return ORBGPU_E_UNSUPPORTED; }
-    ORBGPU_CUDA_CHECK(encode_plane_map(&fastMaps.m[l], e->dPyr + G.pyrOffset, G.pitch, G.rows, G.planeBytes, e->p.max_batch,
-                                       G.fastBoxW, G.fastBoxH));
-  }
+  for (int l = 0; l < T.nlevels; l++)
+    if (T.lv[l].wCell > 124 || T.lv[l].hCell > 63) {      // cannot happen: a cell is 30 .. 59 pixels by construction (ORBextractor.cc:751-754)
+      set_error("internal: FAST cell %dx%d does not fit a strip", T.lv[l].wCell, T.lv[l].hCell);
+      return ORBGPU_E_UNSUPPORTED;
+    }
   ORBGPU_CUDA_CHECK(cudaStreamSynchronize(e->stream));
   if (tabs.size() > e->tabsCap) {
     if (e->dTabs) cudaFree(e->dTabs);
@@ -312,7 +305,7 @@ int configure(orbgpu_extractor *e, int w, int h) {
     ORBGPU_CUDA_CHECK(octree_configure_lat(octMax[d]));
     ORBGPU_CUDA_CHECK(fast_configure(fastMax[d]));
   }
-  e->T = T; e->ntiles = (int)tiles.size(); e->fastCfg = fc; e->fastMaps = fastMaps; e->octSmem = octSmem;
+  e->T = T; e->ntiles = (int)tiles.size(); e->fastCfg = fc; e->octSmem = octSmem;
   e->blurMaps = blurMaps; e->nBlurTiles = (int)blurTiles.size();
   e->rzMaps = rzMaps; e->rzSlotBytes = rzSlot;
   for (int l = 0; l < kMaxLevels; l++) { e->rzTileOff[l] = rzOff[l]; e->rzTileCnt[l] = rzCnt[l]; }
@@ -335,10 +328,10 @@ int run_extract_range(orbgpu_extractor *e, const uint8_t *dImages, int imgBase, 
   cudaStream_t s = e->stream;
   ORBGPU_CUDA_CHECK(cudaMemsetAsync(e->dCandCount + (size_t)imgBase * kMaxLevels, 0, sizeof(int) * kMaxLevels * batch, s));
   ORBGPU_CUDA_CHECK(cudaMemsetAsync(e->dSelCount + (size_t)imgBase * kMaxLevels, 0, sizeof(int) * kMaxLevels * batch, s));
-  // Two streams per batch: the blur only needs the pyramid, so it runs on a side stream next to FAST and the octree and joins
-  // before the descriptor kernel.  FAST is bound by the ALU pipe, the blur by issue slots, the octree by latency: the blur fills
-  // FAST's tail and the octree's idle slots (+5 % frames/s).  (Also moving the pyramid chain of levels 1 .. 7 to the side stream
-  // with FAST split into level 0 / the rest was measured and gives nothing more: those kernels compete for the same issue slots.)
+  // Two streams per batch: the blur only needs the pyramid, the descriptor kernel needs the blur and the octree.  FAST fills
+  // every SM on its own (ALU pipe, 128+ registers per thread), so a blur launched next to it only queues behind or in front
+  // of it; the octree, however, is a latency-bound kernel of batch x levels CTAs that leaves most of the GPU idle.  The blur
+  // therefore starts on the side stream when FAST has finished, runs next to the octree, and joins before the descriptors.
   // With per-stage timing on, everything stays on one stream so that the stage timers remain meaningful.
   static const bool noOverlap = getenv("ORBGPU_NO_OVERLAP") != nullptr;
   const bool overlap = !noOverlap && !e->profiling;
@@ -357,12 +350,12 @@ int run_extract_range(orbgpu_extractor *e, const uint8_t *dImages, int imgBase, 
     ORBGPU_CUDA_CHECK(launch_import_level0(e->T, B, dImages, rowStep, imgStep, imgBase, batch, s));
     int rc = pyramid_rest(s);
     if (rc) return rc;
+    ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->dTiles, e->ntiles, e->fastCfg, imgBase, batch, s));
     ORBGPU_CUDA_CHECK(cudaEventRecord(e->evFork, s));
-    ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(e->side, e->evFork, 0));
+    ORBGPU_CUDA_CHECK(lat ? launch_octree_lat(e->T, B, imgBase, batch, e->octSmem, s) : launch_octree(e->T, B, imgBase, batch, e->octSmem, s));
+    ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(e->side, e->evFork, 0));     // the octree's CTAs are placed first, the blur fills the rest
     ORBGPU_CUDA_CHECK(launch_blur(e->T, B, e->blurMaps, e->dBlurTiles, e->nBlurTiles, imgBase, batch, e->side));
     ORBGPU_CUDA_CHECK(cudaEventRecord(e->evJoin, e->side));
-    ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->fastMaps, e->dTiles, e->ntiles, e->fastCfg, imgBase, batch, s));
-    ORBGPU_CUDA_CHECK(lat ? launch_octree_lat(e->T, B, imgBase, batch, e->octSmem, s) : launch_octree(e->T, B, imgBase, batch, e->octSmem, s));
     ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(s, e->evJoin, 0));
     ORBGPU_CUDA_CHECK(lat ? launch_describe_lat(e->T, B, imgBase, batch, s) : launch_describe(e->T, B, imgBase, batch, s));
     return ORBGPU_OK;
@@ -373,7 +366,7 @@ int run_extract_range(orbgpu_extractor *e, const uint8_t *dImages, int imgBase, 
     int rc = pyramid_rest(s);
     if (rc) return rc;
   }
-  { StageTimer t(e, 1); ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->fastMaps, e->dTiles, e->ntiles, e->fastCfg, imgBase, batch, s)); }
+  { StageTimer t(e, 1); ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->dTiles, e->ntiles, e->fastCfg, imgBase, batch, s)); }
   { StageTimer t(e, 2); ORBGPU_CUDA_CHECK(lat ? launch_octree_lat(e->T, B, imgBase, batch, e->octSmem, s) : launch_octree(e->T, B, imgBase, batch, e->octSmem, s)); }
   { StageTimer t(e, 3); ORBGPU_CUDA_CHECK(launch_blur(e->T, B, e->blurMaps, e->dBlurTiles, e->nBlurTiles, imgBase, batch, s)); }
   { StageTimer t(e, 4); ORBGPU_CUDA_CHECK(lat ? launch_describe_lat(e->T, B, imgBase, batch, s) : launch_describe(e->T, B, imgBase, batch, s)); }

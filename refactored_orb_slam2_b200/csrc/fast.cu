@@ -11,52 +11,54 @@
 //   rectangle (cv::FAST scores pixels outside the rectangle, and non-corners, as 0).
 //   t = iniThFAST if the cell has at least one survivor at iniThFAST, else minThFAST.
 //
-// One CTA = up to kFastCellsPerTile horizontally adjacent cells of one cell row of one level of one
-// image.  The source window (+3 px ring apron) is brought into shared memory by ONE TMA tensor copy
-// (cp.async.bulk.tensor.3d on the level's [batch][rows][pitch] u8 tensor map, completion on an
-// mbarrier).  TMA needs the window's first column on a 16-byte boundary, so pixels are grouped by
-// fours on the PADDED plane's 4-byte grid (groups sit on 32-bit words in shared memory) and the up
-// to 3 + 3 pixels a row of groups overhangs the tile are masked out.  The u8 window is unpacked ONCE per tile into two
-// u16 planes — plane A holds pixel pairs (2j, 2j+1) per 32-bit word, plane B the pairs (2j+1, 2j+2) — so that every ring
-// pixel pair of a thread's two adjacent pixels, at any horizontal offset, is one aligned shared-memory word that is already
-// the packed u16x2 operand of the arithmetic (no per-use PRMT / mask: the unpack costs 1 ALU op per pixel instead of ~13).
-// A thread owns 4 horizontally adjacent pixels = two such pairs: 22 LDS (64-bit where the second pair's word sits next to
-// the first's) fetch both rings and centres, and the arc margins come from the 3-input VIMNMX3.S16x2 min/max of sm_100a
-// (groups of four arcs around their shared six pixels, 68 ops per pixel pair for both polarities).  The TMA copy of the next
-// tile is issued as soon as the unpack has released the u8 window, so it overlaps the whole margin / NMS / emit phase.  Scores (margin - minTh, 0 = not a corner at minTh) go to a
-// shared u8 tile and the coordinates of the non-zero ones to a shared queue (warp-aggregated
-// reservation); NMS and the per-cell threshold fallback run over that queue only; survivors are
-// staged in shared memory and appended to the level's candidate list with one global atomic per CTA.
+// Execution: ONE WARP = ONE STRIP = up to four horizontally adjacent cells of one cell row of one level of one image, at
+// most 128 pixels wide; the warp marches down the strip's rows and never meets another warp (no shared-memory pixel
+// tiles, no CTA barrier).  A lane owns 4 horizontally adjacent pixels = two packed s16x2 pixel pairs P, Q on the padded
+// plane's 4-byte grid and keeps the 7 x 10 pixel neighbourhood of its pixels IN REGISTERS as a rolling window of seven
+// rows x nine packed pair words (pairs starting at x-3 .. x+5): every step loads one new row (three coalesced 32-bit
+// words per lane, issued one step ahead), unpacks it ONCE with nine PRMT, and all 2 x 16 ring operands of the
+// step are then plain registers — the 3-input VIMNMX3.S16x2 arc networks (68 per pixel pair) are the only real work
+// left on the ALU pipe.  The loop is unrolled seven-fold so that the window rotates by register renaming.
+// Scores (margin - minTh, 0 = not a corner at minTh) stay in registers as well: NMS of row y-1 runs when row y is
+// scored, horizontal neighbours come from the adjacent lanes by shuffle, cell borders are per-lane constant masks,
+// survivors are appended to the warp's shared-memory stage list (4 bytes each), and at the end of the strip the warp
+// applies the per-cell threshold fallback and appends to the level's candidate list with one global atomic per 32.
 // Candidate order in HBM is arbitrary: the octree only needs each candidate's position in the
 // reference's cell-major order to break response ties, and that is a function of (x, y).
 #include <cstdlib>
 
 #include "internal.cuh"
-#include "tma.cuh"
 
 namespace orbgpu {
 
 namespace {
 
-constexpr int kThreads = ORBGPU_FAST_THREADS;
-constexpr int kWarps = kThreads / 32;
+constexpr int kWarps = ORBGPU_FAST_WARPS;
+constexpr int kThreads = kWarps * 32;
 
 __device__ __forceinline__ unsigned mn3(unsigned a, unsigned b, unsigned c) { return __vimin3_s16x2(a, b, c); }
 __device__ __forceinline__ unsigned mx3(unsigned a, unsigned b, unsigned c) { return __vimax3_s16x2(a, b, c); }
 __device__ __forceinline__ unsigned mx2(unsigned a, unsigned b) { return __vmaxs2(a, b); }
+// The ALU pipe (VIMNMX3, LOP3, PRMT, IADD3, SHF: 64 lanes / clk / SM) is this kernel's bound; bitwise NOT and the 24-bit
+// right shift are therefore written as integer multiply-adds, which issue on the otherwise idle FMA pipe:
+// ~x = x * -1 + -1  and  x >> 24 = hi32(x * 256).  The multipliers arrive as kernel arguments (FmaConsts) — with literal
+// constants ptxas folds both back into IADD3 / SHF on the ALU pipe.
+struct FmaConsts { unsigned ones, two8; };          // 0xffffffff, 256
+__device__ __forceinline__ unsigned not_fma(unsigned x, const FmaConsts &K) { return x * K.ones + K.ones; }
+__device__ __forceinline__ unsigned top_byte_fma(unsigned x, const FmaConsts &K) { return __umulhi(x, K.two8); }
 
-// Arc margins (packed s16x2) of two horizontally adjacent pixels from their 16 ring values d[k] (packed u16x2, ring order
-// of cv::FAST 9/16: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)) and
-// their centres c.  min / max commute with subtracting the centre, so the sliding-window networks run on the RAW ring pixels
-// and the centre is subtracted once from the two extrema:
+// Arc margins (packed s16x2) of two pixels from their 16 ring values d[k] (packed u16x2, ring order of cv::FAST 9/16:
+// (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)) and their centres c.
+// min / max commute with subtracting the centre, so the sliding-window networks run on the RAW ring pixels and the
+// centre is subtracted once from the two extrema:
 //   bright margin = max_arcs min_arc(ring) - centre ,  dark margin = centre - min_arcs max_arc(ring).
-// Returns max(margin - minTh, 0) per halfword; k1 = (1 - minTh) in both halves.  With ~v = -v - 1 per halfword,
-//   margin - minTh = max(bright + (~c + k1), (c + k1) + ~dark), and the final max with 0 rides on the same instruction.
-__device__ __forceinline__ unsigned score_of_ring(const unsigned (&d)[16], unsigned c, unsigned k1) {
-  // The four arcs that start at k .. k+3 share the six pixels k+3 .. k+8, and max(min(S, x), min(S, y)) = min(S, max(x, y)):
-  //   max_j min(arc k+j) = min(ring[k+3 .. k+8], max(T[k], min(r[k+1], r[k+2], r[k+9]), min(r[k+2], r[k+9], r[k+10]), T[k+9]))
-  // with T[j] = min(r[j], r[j+1], r[j+2]).  Eight T's serve all four groups (T[k+4] is also half of group k's shared
-  // part): 34 three-input operations per polarity instead of the 40 of a plain sliding window.
+// The four arcs that start at k .. k+3 share the six pixels k+3 .. k+8, and max(min(S, x), min(S, y)) = min(S, max(x, y)):
+//   max_j min(arc k+j) = min(ring[k+3 .. k+8], max(T[k], min(r[k+1], r[k+2], r[k+9]), min(r[k+2], r[k+9], r[k+10]), T[k+9]))
+// with T[j] = min(r[j], r[j+1], r[j+2]); eight T's serve all four groups (T[k+4] is also half of group k's shared part):
+// 34 three-input operations per polarity.  Returns max(margin - minTh, 0) per halfword; k1 = (1 - minTh) in both
+// halves.  With ~v = -v - 1 per halfword, margin - minTh = max(bright + (~c + k1), (c + k1) + ~dark), and the final max
+// with 0 rides on the same instruction.
+__device__ __forceinline__ unsigned score_of_ring(const unsigned (&d)[16], unsigned c, unsigned k1, const FmaConsts &K) {
   unsigned tn[16], tx[16];
 #pragma unroll
   for (int k = 0; k < 16; k += 4) {
@@ -78,276 +80,242 @@ __device__ __forceinline__ unsigned score_of_ring(const unsigned (&d)[16], unsig
   }
   const unsigned bright = mx2(mx3(gb[0], gb[1], gb[2]), gb[3]);
   const unsigned dark = __vmins2(mn3(gd[0], gd[1], gd[2]), gd[3]);
-  return __viaddmax_s16x2_relu(bright, __vadd2(~c, k1), __vadd2(__vadd2(c, k1), ~dark));
+  return __viaddmax_s16x2_relu(bright, __vadd2(not_fma(c, K), k1), __vadd2(__vadd2(c, k1), not_fma(dark, K)));
 }
 
-// Geometry of one work item = one tile of one image.
-struct TileGeom {
-  int level, img, X0, Y0, TW, TH, gx0, offL, groups, bx, lead;
-};
-// (ti, img) = tile index within an image and image of the work item; the caller steps them without dividing
-__device__ __forceinline__ TileGeom tile_geom(const LevelTable *T, const int4 *tiles, int ti, int img) {
-  TileGeom t;
-  t.img = img;
-  const int4 tile = tiles[ti];                            // (level, cell row i, first cell column j0, cell count)
-  t.level = tile.x;
-  const LevelGeom &G = T->lv[t.level];
-  // detection rectangle of the tile, level coordinates
-  t.X0 = kEdge + tile.z * G.wCell; t.Y0 = kEdge + tile.y * G.hCell;
-  const int X1 = min(kEdge + (tile.z + tile.w) * G.wCell, G.w - kEdge);
-  const int Y1 = min(t.Y0 + G.hCell, G.h - kEdge);
-  t.TW = X1 - t.X0; t.TH = Y1 - t.Y0;
-  // 4-pixel groups on the padded plane's 4-byte grid
-  t.gx0 = (t.X0 + kEdge) & ~3;                            // padded column of the first group
-  t.offL = (t.X0 + kEdge) - t.gx0;                        // tile x = score column - offL
-  t.groups = (t.offL + t.TW + 3) >> 2;
-  t.bx = (t.gx0 - 4) & ~15;                               // window origin: 16-byte aligned for TMA
-  t.lead = (t.gx0 - 4) - t.bx;                            // 0, 4, 8 or 12
-  return t;
+// ring position k -> (dx, dy), dy positive = down
+__host__ __device__ constexpr int ring_dx(int k) { return k <= 3 ? k : k <= 5 ? 3 : k <= 8 ? 8 - k : k <= 11 ? 8 - k : k <= 13 ? -3 : k - 16; }
+__host__ __device__ constexpr int ring_dy(int k) { return k <= 1 ? 3 : k <= 4 ? 4 - k : k <= 7 ? 4 - k : k <= 9 ? -3 : k <= 12 ? k - 12 : k <= 14 ? k - 12 : 3; }
+static_assert(ring_dx(0) == 0 && ring_dx(1) == 1 && ring_dx(2) == 2 && ring_dx(3) == 3 && ring_dx(4) == 3 && ring_dx(5) == 3 && ring_dx(6) == 2 &&
+              ring_dx(7) == 1 && ring_dx(8) == 0 && ring_dx(9) == -1 && ring_dx(10) == -2 && ring_dx(11) == -3 && ring_dx(12) == -3 &&
+              ring_dx(13) == -3 && ring_dx(14) == -2 && ring_dx(15) == -1, "cv::FAST 9/16 ring, x offsets");
+static_assert(ring_dy(0) == 3 && ring_dy(1) == 3 && ring_dy(2) == 2 && ring_dy(3) == 1 && ring_dy(4) == 0 && ring_dy(5) == -1 && ring_dy(6) == -2 &&
+              ring_dy(7) == -3 && ring_dy(8) == -3 && ring_dy(9) == -3 && ring_dy(10) == -2 && ring_dy(11) == -1 && ring_dy(12) == 0 &&
+              ring_dy(13) == 1 && ring_dy(14) == 2 && ring_dy(15) == 3, "cv::FAST 9/16 ring, y offsets");
+
+struct Raw { unsigned w0, w1, w2; };   // bytes x-4 .. x+7 of one row around a lane's four pixels x .. x+3
+
+__device__ __forceinline__ Raw load_row(const uint8_t *p) {
+  Raw r;
+  r.w0 = __ldg(reinterpret_cast<const unsigned *>(p) - 1);
+  r.w1 = __ldg(reinterpret_cast<const unsigned *>(p));
+  r.w2 = __ldg(reinterpret_cast<const unsigned *>(p) + 1);
+  return r;
+}
+// the nine packed u16x2 pixel pairs (x+s, x+s+1), s = -3 .. 5, of one row: win[s + 3]
+__device__ __forceinline__ void unpack_row(const Raw &r, unsigned (&win)[9], const FmaConsts &K) {
+  win[0] = __byte_perm(r.w0, 0u, 0x4241u);
+  win[1] = __byte_perm(r.w0, 0u, 0x4342u);
+  win[2] = __byte_perm(top_byte_fma(r.w0, K), r.w1, 0x1410u);         // (w0.b3, w1.b0): the shifted word supplies the zero bytes
+  win[3] = __byte_perm(r.w1, 0u, 0x4140u);
+  win[4] = __byte_perm(r.w1, 0u, 0x4241u);
+  win[5] = __byte_perm(r.w1, 0u, 0x4342u);
+  win[6] = __byte_perm(top_byte_fma(r.w1, K), r.w2, 0x1410u);
+  win[7] = __byte_perm(r.w2, 0u, 0x4140u);
+  win[8] = __byte_perm(r.w2, 0u, 0x4241u);
 }
 
-// Persistent CTAs: each walks items blockIdx.x, blockIdx.x + gridDim.x, ...
+// Pulls the line(s) of a later row towards L1 without tying up a register: the three LDGs of that row then hit.  Rows past
+// the strip still lie inside the padded plane (19 apron rows follow the last detection row).
+constexpr int kPrefetchRows = ORBGPU_FAST_PREFETCH;
+constexpr int kAhead = ORBGPU_FAST_AHEAD;             // rows between a row's register loads and its first use (1 .. 5)
+__device__ __forceinline__ void prefetch_l1(const uint8_t *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ int atom_add_shared(int *p, int v) {   // plain ATOMS (keeps nvcc from expanding it into a warp scan)
+  int old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+  return old;
+}
+
+// NMS state a lane carries between rows: scores of the previous row, its left / right neighbour maximum, and the
+// 3-wide row maxima of the previous two rows
+struct NmsState { unsigned sP, sQ, sideP, sideQ, h3P, h3Q, h3ppP, h3ppQ; };
+struct LaneMasks { unsigned mLP, mRP, mLQ, mRQ, vP, vQ; };
+
+// Decides row `yPrev` (scores in st.s*) now that the row below it is known (h3 of that row in h3P / h3Q; pass 0 below
+// the strip), and appends the survivors to the warp's stage list as  x | y << 7 | score << 13.  About 2 % of the pixels
+// survive, so the append is a short loop over the lane's set bits behind one rarely taken branch.
+__device__ __forceinline__ void nms_row(const NmsState &st, unsigned h3P, unsigned h3Q, const LaneMasks &M, int x0, int yPrev,
+                                        unsigned *stage, int *stageCount, int stageCap, const FmaConsts &K) {
+  const unsigned nbP = mx3(st.h3ppP, st.sideP, h3P), nbQ = mx3(st.h3ppQ, st.sideQ, h3Q);
+  // s + ~nb = s - nb - 1 per halfword: sign clear  <=>  s > nb (and then s > 0)
+  const unsigned kP = ~__vadd2(st.sP, not_fma(nbP, K)) & M.vP, kQ = ~__vadd2(st.sQ, not_fma(nbQ, K)) & M.vQ;   // bit 15 / 31 per surviving pixel
+  if ((kP | kQ) != 0u) {
+    unsigned bits = ((kP >> 15) & 1u) | ((kP >> 30) & 2u) | ((kQ >> 13) & 4u) | ((kQ >> 28) & 8u);
+    const unsigned row = (unsigned)yPrev << 7;
+    do {
+      const int j = __ffs((int)bits) - 1;
+      bits &= bits - 1u;
+      const unsigned w = (j & 2) ? st.sQ : st.sP;
+      const unsigned s = (j & 1) ? (w >> 16) : (w & 0xffffu);
+      const int at = atom_add_shared(stageCount, 1);
+      if (at < stageCap) stage[at] = (unsigned)(x0 + j) | row | (s << 13);
+    } while (bits != 0u);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, ORBGPU_FAST_CTAS_PER_SM)
-k_fast_cells(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict__ T, const int4 *__restrict__ tiles,
-             int ntiles, int totalItems, int imgBase, Cand *__restrict__ cand, int *__restrict__ candCount,
-             unsigned *__restrict__ status, const FastConfig cfg) {
-  extern __shared__ uint8_t smemRaw[];
-  __shared__ __align__(8) unsigned long long sBar;
-  __shared__ int sCellCnt[kFastCellsPerTile];
-  __shared__ int sQueued, sKept;
-
+k_fast_strips(const LevelTable *__restrict__ T, const int4 *__restrict__ strips, int nstrips, int totalItems, int imgBase,
+              const uint8_t *__restrict__ pyr, Cand *__restrict__ cand, int *__restrict__ candCount, unsigned *__restrict__ status,
+              int stageCap, const FmaConsts K) {
+  extern __shared__ unsigned sStageAll[];            // [kWarps][stageCap]
+  __shared__ int sCount[kWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * kWarps + warp;
+  if (item >= totalItems) return;                    // warps are independent: no CTA barrier anywhere below
+  const int imgRel = item / nstrips, img = imgBase + imgRel;
+  const int4 strip = strips[item - imgRel * nstrips];     // (level, cell row i, first cell column j0, cell count)
+  const int level = strip.x;
+  const LevelGeom &G = T->lv[level];
   const int iniTh = T->iniTh, minTh = T->minTh;
-  const int tid = threadIdx.x;
-  uint8_t *smem = smemRaw + ((128u - (smem_u32(smemRaw) & 127u)) & 127u);   // TMA destination: 128-byte aligned
-  // [u8 window: imgBytes][plane A: 2 x imgBytes][plane B: 2 x imgBytes][scores][queue]; the survivor stage list aliases
-  // plane A, which is dead once the margins are computed
-  unsigned *sPlaneA = reinterpret_cast<unsigned *>(smem + cfg.imgBytes);
-  unsigned *sPlaneB = reinterpret_cast<unsigned *>(smem + 3 * cfg.imgBytes);
-  // u8 scores, pitch cfg.scorePitch, column 0 = padded column gx0; one halo row above / below (kept zero) and one halo
-  // column on each side (always masked by the cell test) so that NMS reads its 8 neighbours without bounds checks
-  uint8_t *sScore = smem + 5 * cfg.imgBytes + cfg.scorePitch + 4;
-  unsigned short *sQueue = reinterpret_cast<unsigned short *>(smem + 5 * cfg.imgBytes + cfg.scoreBytes);   // (row << 8 | column) of non-zero scores
-  Cand *sStage = reinterpret_cast<Cand *>(sPlaneA);
-  const int sp = cfg.scorePitch;
+  // detection rectangle of the strip, level coordinates
+  const int X0 = kEdge + strip.z * G.wCell, Y0 = kEdge + strip.y * G.hCell;
+  const int X1 = min(kEdge + (strip.z + strip.w) * G.wCell, G.w - kEdge), Y1 = min(Y0 + G.hCell, G.h - kEdge);
+  const int TW = X1 - X0, TH = Y1 - Y0;
+  const int gx0 = (X0 + kEdge) & ~3;                 // padded column of lane 0's first pixel (4-byte grid)
+  const int offL = (X0 + kEdge) - gx0;               // strip x = 4 * lane + j - offL
+  const int wCell = G.wCell;
+  unsigned *stage = sStageAll + warp * stageCap;
+  int *stageCount = &sCount[warp];
+  if (lane == 0) *stageCount = 0;
+  __syncwarp();
 
-  if (tid == 0) {
-    mbar_init(&sBar, 1);
-    mbar_fence_init();
+  // per-lane constants: which of the lane's four pixels lie in the strip, their cell, and whether their left / right
+  // neighbour column belongs to the same cell rectangle
+  const int x0 = 4 * lane - offL;
+  LaneMasks M = {0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int x = x0 + j;
+    const bool valid = x >= 0 && x < TW;
+    const int c = (x >= wCell) + (x >= 2 * wCell) + (x >= 3 * wCell);
+    const int cx0 = c * wCell, cx1 = min(cx0 + wCell, TW);
+    const unsigned half = 0xffffu << (16 * (j & 1));
+    const bool l = valid && x > cx0, r = valid && x + 1 < cx1;
+    if (j < 2) { M.mLP |= l ? half : 0u; M.mRP |= r ? half : 0u; M.vP |= valid ? (half & 0x80008000u) : 0u; }
+    else       { M.mLQ |= l ? half : 0u; M.mRQ |= r ? half : 0u; M.vQ |= valid ? (half & 0x80008000u) : 0u; }
   }
-  __syncthreads();
-  if (tid == 0 && (int)blockIdx.x < totalItems) {
-    const TileGeom n = tile_geom(T, tiles, (int)blockIdx.x % ntiles, imgBase + (int)blockIdx.x / ntiles);
-    const LevelGeom &Gn = T->lv[n.level];
-    mbar_expect_tx(&sBar, (unsigned)(Gn.fastBoxW * Gn.fastBoxH));
-    tma_load_3d(smem, &maps.m[n.level], n.bx, n.Y0 - 3 + kEdge, n.img, &sBar);
-  }
-  // work item = (tile ti of image imgCur); stepping by gridDim.x items without a division per tile
-  int ti = (int)blockIdx.x % ntiles, imgCur = imgBase + (int)blockIdx.x / ntiles;
-  const int stepImg = (int)gridDim.x / ntiles, stepTi = (int)gridDim.x - stepImg * ntiles;
 
-  int iter = 0;
-  for (int item = blockIdx.x; item < totalItems; item += gridDim.x, iter++) {
-    const TileGeom tg = tile_geom(T, tiles, ti, imgCur);
-    int tiNext = ti + stepTi, imgNext = imgCur + stepImg;
-    if (tiNext >= ntiles) { tiNext -= ntiles; imgNext++; }
-    const LevelGeom &G = T->lv[tg.level];
-    const int level = tg.level, img = tg.img, X0 = tg.X0, Y0 = tg.Y0, TW = tg.TW, TH = tg.TH;
-    const int offL = tg.offL, groups = tg.groups, lead = tg.lead;
-    const int bw = G.fastBoxW;
-    if (tid == 0) { sQueued = 0; sKept = 0; }
-    if (tid < kFastCellsPerTile) sCellCnt[tid] = 0;
-    for (int i = tid; i < 2 * (sp >> 2); i += kThreads) {   // zero the halo rows -1 and TH
-      const int half = sp >> 2;
-      unsigned *rowp = reinterpret_cast<unsigned *>(sScore + (i < half ? -1 : TH) * sp - 4);
-      rowp[i < half ? i : i - half] = 0u;
-    }
-    mbar_wait(&sBar, iter & 1);
+  const unsigned k1 = ((unsigned)(1 - minTh) & 0xffffu) * 0x00010001u;
+  const int iniS = iniTh - minTh;                    // score > iniS  <=>  margin > iniTh
+  const int pitch = G.pitch;
+  const uint8_t *rowPtr = pyr + G.pyrOffset + (size_t)img * G.planeBytes + (size_t)(Y0 - 3 + kEdge) * pitch + gx0 + 4 * lane;
+  // prefetch addresses cover the whole 136-byte span the warp reads per row (lane 0 its left word, lane 31 its right word)
+  const int pfOff = lane == 31 ? 4 : -4;
 
-    // ---- unpack the u8 window into the two u16 planes (the window's rows are contiguous: word i + 1 follows word i, and the
-    // pair that straddles a row end is never read)
-    {
-      const unsigned *src = reinterpret_cast<const unsigned *>(smem);
-      uint2 *dA = reinterpret_cast<uint2 *>(sPlaneA), *dB = reinterpret_cast<uint2 *>(sPlaneB);
-      const int nwords = (bw >> 2) * (TH + 6);
-      for (int i = tid; i < nwords; i += kThreads) {
-        const unsigned w0 = src[i], w1 = src[i + 1];
-        dA[i] = make_uint2(__byte_perm(w0, 0u, 0x4140u), __byte_perm(w0, 0u, 0x4342u));
-        dB[i] = make_uint2(__byte_perm(w0, 0u, 0x4241u), __byte_perm(w0, w1, 0x4443u) & 0x00ff00ffu);
-      }
-    }
-    __syncthreads();                                       // planes complete; the u8 window and last item's stage list are free
-    if (tid == 0) {
-      const int next = item + gridDim.x;
-      if (next < totalItems) {
-        const TileGeom n = tile_geom(T, tiles, tiNext, imgNext);
-        const LevelGeom &Gn = T->lv[n.level];
-        mbar_expect_tx(&sBar, (unsigned)(Gn.fastBoxW * Gn.fastBoxH));
-        tma_load_3d(smem, &maps.m[n.level], n.bx, n.Y0 - 3 + kEdge, n.img, &sBar);
-      }
-    }
-
-    // ---- arc margins: work items = (row, 4-pixel group) pairs, dealt round-robin to the CTA's threads so that every
-    // lane is busy whatever the tile shape; corners at minTh are queued
-    const unsigned k1 = ((unsigned)(1 - minTh) & 0xffffu) * 0x00010001u;
-    const int items = TH * groups;
-    const int stepY = kThreads / groups, stepG = kThreads - stepY * groups;
-    const int pw = bw >> 1;                                // plane pitch in 32-bit words
-    int y = tid / groups, g = tid - y * groups;
-    for (int i0 = 0; i0 < items; i0 += kThreads) {
-      unsigned packed = 0;
-      if (i0 + tid < items) {
-        // word index of the thread's first pixel pair (window column lead + 4g + 4, always even); P = that pair, Q = the next
-        const int a = y * pw + ((lead + 4) >> 1) + 2 * g;
-        const unsigned *A = sPlaneA + a, *B = sPlaneB + a;
-        unsigned dP[16], dQ[16];
-        {   // rows y-3 / y+3 (ring 7, 8, 9 / 15, 0, 1): dx = +1, 0, -1
-          const uint2 a0 = *reinterpret_cast<const uint2 *>(A), b0 = *reinterpret_cast<const uint2 *>(B);
-          const unsigned bm = B[-1];
-          dP[8] = a0.x; dQ[8] = a0.y; dP[7] = b0.x; dQ[7] = b0.y; dP[9] = bm; dQ[9] = b0.x;
-          const uint2 a6 = *reinterpret_cast<const uint2 *>(A + 6 * pw), b6 = *reinterpret_cast<const uint2 *>(B + 6 * pw);
-          const unsigned bm6 = B[6 * pw - 1];
-          dP[0] = a6.x; dQ[0] = a6.y; dP[1] = b6.x; dQ[1] = b6.y; dP[15] = bm6; dQ[15] = b6.x;
+  unsigned win[7][9];                                // rolling window: row r of the strip's source rows lives in slot r % 7
+  NmsState st = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+  const int nRows = TH + 6;                          // source rows Y0 - 3 .. Y1 + 2
+#pragma unroll
+  for (int i = 0; i < kPrefetchRows; i++) prefetch_l1(rowPtr + (kAhead + i) * pitch + pfOff);
+  // raw rows in flight: row r is unpacked from raw[r % 7] while row r + kAhead is being loaded into raw[(r + kAhead) % 7] (a
+  // ring indexed like the window, so no register is ever copied from a load's destination before its data is needed)
+  Raw raw[7];
+#pragma unroll
+  for (int i = 0; i < kAhead; i++) raw[i] = load_row(rowPtr + i * pitch);
+  for (int r0 = 0; r0 < nRows; r0 += 7) {
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+      const int r = r0 + k;
+      if (r < nRows) {
+        raw[(k + kAhead) % 7] = load_row(rowPtr + kAhead * pitch);       // row r + kAhead (always inside the padded plane)
+        prefetch_l1(rowPtr + (kAhead + kPrefetchRows) * pitch + pfOff);          // and later rows on their way from HBM / L2 into L1
+        rowPtr += pitch;
+        unpack_row(raw[k], win[k], K);
+        if (r >= 6) {
+          // pixel row y = r - 6: its ring rows y-3 .. y+3 are the source rows r-6 .. r = slots (k + 1 + i) % 7
+          unsigned dP[16], dQ[16];
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            const int slot = (k + 4 + ring_dy(i)) % 7;
+            dP[i] = win[slot][ring_dx(i) + 3];
+            dQ[i] = win[slot][ring_dx(i) + 5];
+          }
+          const unsigned sP = score_of_ring(dP, win[(k + 4) % 7][3], k1, K);
+          const unsigned sQ = score_of_ring(dQ, win[(k + 4) % 7][5], k1, K);
+          // horizontal neighbours: (x-1, x) / (x+1, x+2) / (x+3, x+4) as packed pairs, cell borders masked out
+          const unsigned prevQ = __shfl_up_sync(0xffffffffu, sQ, 1), nextP = __shfl_down_sync(0xffffffffu, sP, 1);
+          const unsigned mid = __byte_perm(sP, sQ, 0x5432u);
+          const unsigned LP = __byte_perm(prevQ, sP, 0x5432u) & M.mLP, RP = mid & M.mRP;
+          const unsigned LQ = mid & M.mLQ, RQ = __byte_perm(sQ, nextP, 0x5432u) & M.mRQ;
+          const unsigned h3P = mx3(LP, sP, RP), h3Q = mx3(LQ, sQ, RQ);
+          nms_row(st, h3P, h3Q, M, x0, r - 7, stage, stageCount, stageCap, K);     // row y - 1 (nothing survives for y = 0)
+          st.h3ppP = st.h3P; st.h3ppQ = st.h3Q; st.h3P = h3P; st.h3Q = h3Q;
+          st.sP = sP; st.sQ = sQ; st.sideP = mx2(LP, RP); st.sideQ = mx2(LQ, RQ);
         }
-        {   // rows y-2 / y+2 (ring 6, 10 / 2, 14): dx = +2, -2
-          const uint2 a1 = *reinterpret_cast<const uint2 *>(A + pw);
-          dP[6] = a1.y; dQ[6] = A[pw + 2]; dP[10] = A[pw - 1]; dQ[10] = a1.x;
-          const uint2 a5 = *reinterpret_cast<const uint2 *>(A + 5 * pw);
-          dP[2] = a5.y; dQ[2] = A[5 * pw + 2]; dP[14] = A[5 * pw - 1]; dQ[14] = a5.x;
-        }
-        {   // rows y-1 / y+1 (ring 5, 11 / 3, 13): dx = +3, -3
-          const uint2 b2 = *reinterpret_cast<const uint2 *>(B + 2 * pw - 2);
-          dP[5] = B[2 * pw + 1]; dQ[5] = B[2 * pw + 2]; dP[11] = b2.x; dQ[11] = b2.y;
-          const uint2 b4 = *reinterpret_cast<const uint2 *>(B + 4 * pw - 2);
-          dP[3] = B[4 * pw + 1]; dQ[3] = B[4 * pw + 2]; dP[13] = b4.x; dQ[13] = b4.y;
-        }
-        // row y (ring 4, 12): dx = +3, -3, and the centres
-        const uint2 b3 = *reinterpret_cast<const uint2 *>(B + 3 * pw - 2);
-        dP[4] = B[3 * pw + 1]; dQ[4] = B[3 * pw + 2]; dP[12] = b3.x; dQ[12] = b3.y;
-        const uint2 c = *reinterpret_cast<const uint2 *>(A + 3 * pw);
-        // score = max(margin, minTh) - minTh: 0 when the pixel is not a corner at minTh
-        const unsigned sA = score_of_ring(dP, c.x, k1);
-        const unsigned sB = score_of_ring(dQ, c.y, k1);
-        // (the up to 3 + 3 pixels of the first / last group outside the tile's detection columns are scored and queued like
-        // the rest: NMS never reads them as neighbours — the cell test masks those columns — and drops their own entries)
-        packed = __byte_perm(sA, sB, 0x6420u);
-        *reinterpret_cast<unsigned *>(sScore + y * sp + 4 * g) = packed;
       }
-      // queue the non-zero scores as (row << 8 | score column); one shared-memory reservation per lane that has any
-      if (packed != 0u) {
-        const int mine = (packed & 0xffu ? 1 : 0) + (packed & 0xff00u ? 1 : 0) + (packed & 0xff0000u ? 1 : 0) + (packed >> 24 ? 1 : 0);
-        int at = atomicAdd(&sQueued, mine);
-        const unsigned short e = (unsigned short)((y << 8) | (4 * g));
-        if (packed & 0xffu) sQueue[at++] = e;
-        if (packed & 0xff00u) sQueue[at++] = e + 1;
-        if (packed & 0xff0000u) sQueue[at++] = e + 2;
-        if (packed >> 24) sQueue[at] = e + 3;
-      }
-      y += stepY; g += stepG;
-      if (g >= groups) { g -= groups; y++; }
-    }
-    __syncthreads();
-
-  // ---- NMS inside each cell's rectangle over the queue; survivors go to the stage list, cells count survivors at iniTh
-  const int iniS = iniTh - minTh;                         // score > iniS  <=>  margin > iniTh
-  const int nq = sQueued;
-  for (int i = tid; i < nq; i += kThreads) {
-    const int e = sQueue[i];
-    const int y = e >> 8, sx = e & 0xff;
-    const uint8_t *c0 = sScore + y * sp + sx;
-    const int s = c0[0];
-    const int x = sx - offL;                               // tile coordinate
-    if (x < 0 || x >= TW) continue;                        // group overhang next to the tile
-    const int c = (x >= G.wCell) + (x >= 2 * G.wCell) + (x >= 3 * G.wCell);
-    const int cx0 = c * G.wCell, cx1 = min(cx0 + G.wCell, TW);
-    // neighbours outside the cell's rectangle count as 0: rows -1 / TH are the zero halo, columns are masked
-    const bool left = x > cx0, right = x + 1 < cx1;
-    const int ml = max(max((int)c0[-1], (int)c0[-sp - 1]), (int)c0[sp - 1]);
-    const int mr = max(max((int)c0[1], (int)c0[-sp + 1]), (int)c0[sp + 1]);
-    const int m = max(max((int)c0[-sp], (int)c0[sp]), max(left ? ml : 0, right ? mr : 0));
-    const bool keep = s > m;
-    if (keep) {
-      const int slot = atomicAdd(&sKept, 1);
-      if (slot < cfg.stageCap) {
-        Cand o;
-        o.xy = (unsigned)(X0 + x - kMinBorder) | ((unsigned)(Y0 + y - kMinBorder) << 16);
-        o.resp = (unsigned)(s + minTh - 1) | ((unsigned)c << 16);     // cv::FAST response = margin - 1; cell in the high half
-        sStage[slot] = o;
-      }
-      if (s > iniS) atomicAdd(&sCellCnt[c], 1);
     }
   }
-  __syncthreads();
+  nms_row(st, 0u, 0u, M, x0, TH - 1, stage, stageCount, stageCap, K);              // last row: nothing below it
 
-  // ---- emit: cells with no survivor at iniTh fall back to minTh (ORBextractor.cc:776-780).  Every warp appends its share
-  // of the stage list on its own: ballot, one global atomic per warp round, no CTA-wide barrier on the critical path.
-  const int nk = min(sKept, cfg.stageCap);
-  if (tid == 0 && sKept > cfg.stageCap) atomicOr(status, kStatusCandOverflow);
-  {
-    const int lane = tid & 31;
-    int *counter = &candCount[img * kMaxLevels + level];
-    Cand *out = cand + G.candOffset + (size_t)img * G.candCap;
-    for (int i0 = (tid >> 5) * 32; i0 < nk; i0 += kThreads) {
-      const int i = i0 + lane;
+  // ---- emit: cells with no survivor at iniTh fall back to minTh (ORBextractor.cc:776-780)
+  __syncwarp();
+  const int kept = *stageCount;
+  if (kept > stageCap && lane == 0) atomicOr(status, kStatusCandOverflow);
+  const int nk = min(kept, stageCap);
+  unsigned iniMask = 0u;                             // bit c: cell c of the strip has a survivor above iniTh
+  for (int i = lane; i < nk; i += 32) {
+    const unsigned e = stage[i];
+    const int x = (int)(e & 127u);
+    if ((int)((e >> 13) & 0xffu) > iniS) iniMask |= 1u << ((x >= wCell) + (x >= 2 * wCell) + (x >= 3 * wCell));
+  }
+  iniMask = __reduce_or_sync(0xffffffffu, iniMask);
+  int *counter = &candCount[img * kMaxLevels + level];
+  Cand *out = cand + G.candOffset + (size_t)img * G.candCap;
+  for (int i0 = 0; i0 < nk; i0 += 32) {
+    const int i = i0 + lane;
+    unsigned e = 0u;
+    bool emit = false;
+    if (i < nk) {
+      e = stage[i];
+      const int x = (int)(e & 127u), c = (x >= wCell) + (x >= 2 * wCell) + (x >= 3 * wCell);
+      emit = (int)((e >> 13) & 0xffu) > iniS || !((iniMask >> c) & 1u);
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, emit);
+    if (mask == 0u) continue;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (emit) {
+      const int slot = base + __popc(mask & ((1u << lane) - 1u));
       Cand o;
-      bool emit = false;
-      if (i < nk) {
-        o = sStage[i];
-        const int s = (int)(o.resp & 0xffffu) + 1 - minTh, c = (int)(o.resp >> 16);
-        emit = s > iniS || sCellCnt[c] == 0;
-      }
-      const unsigned mask = __ballot_sync(0xffffffffu, emit);
-      if (mask == 0u) continue;
-      int base = 0;
-      if (lane == 0) base = atomicAdd(counter, __popc(mask));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (emit) {
-        const int slot = base + __popc(mask & ((1u << lane) - 1u));
-        o.resp &= 0xffffu;
-        if (slot < G.candCap) out[slot] = o; else atomicOr(status, kStatusCandOverflow);
-      }
+      o.xy = (unsigned)(X0 + (int)(e & 127u) - kMinBorder) | ((unsigned)(Y0 + (int)((e >> 7) & 63u) - kMinBorder) << 16);
+      o.resp = ((e >> 13) & 0xffu) + (unsigned)minTh - 1u;             // cv::FAST response = margin - 1
+      if (slot < G.candCap) out[slot] = o; else atomicOr(status, kStatusCandOverflow);
     }
-  }
-    __syncthreads();   // stage list (= plane A), queue and counters are free again
-    ti = tiNext; imgCur = imgNext;
   }
 }
 
 }  // namespace
 
-cudaError_t fast_configure(int smemBytes) {
-  return cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
-}
+// Cells per strip of a level: as many (up to 4) as fit 128 pixels including the up to 3 pixels the strip's first
+// 4-pixel group starts before it.
+int fast_cells_per_strip(int wCell) { return wCell <= 31 ? 4 : wCell <= 41 ? 3 : wCell <= 62 ? 2 : 1; }
 
-// Shared-memory budget of the FAST kernel for a level table (whose fastBoxW / fastBoxH are already set).
+// Stage-list entries per warp: NMS survivors are strict 8-neighbour maxima inside one cell rectangle, at most
+// ceil(cw / 2) * ceil(ch / 2) per cell.
 FastConfig fast_make_config(const LevelTable &T) {
-  int wMax = 0, hMax = 0, img = 0;
+  FastConfig c{};
+  int cap = 64;
   for (int l = 0; l < T.nlevels; l++) {
-    wMax = max(wMax, T.lv[l].wCell); hMax = max(hMax, T.lv[l].hCell);
-    img = max(img, T.lv[l].fastBoxW * T.lv[l].fastBoxH);
+    const LevelGeom &G = T.lv[l];
+    cap = max(cap, fast_cells_per_strip(G.wCell) * ((G.wCell + 1) / 2) * ((G.hCell + 1) / 2));
   }
-  FastConfig c;
-  const int tw = kFastCellsPerTile * wMax;
-  c.imgBytes = (img + 4 + 127) & ~127;               // + the word the unpack reads past the last one
-  c.scorePitch = (tw + 3 + 3 + 3) & ~3;             // + the group overhang on both sides
-  c.scoreBytes = (c.scorePitch * (hMax + 2) + 8 + 15) & ~15;   // + halo rows and the 4-byte lead of the halo column
-  c.stageCap = (tw / 2 + kFastCellsPerTile) * (hMax / 2 + 1);   // strict 8-neighbour maxima per cell rectangle: ceil(cw / 2) * ceil(ch / 2)
-  c.queueCap = c.scorePitch * hMax;
-  // window + two u16 planes (the stage list lives in plane A) + scores + queue
-  if (c.stageCap * (int)sizeof(Cand) > 2 * c.imgBytes) c.stageCap = 2 * c.imgBytes / (int)sizeof(Cand);
-  c.smemBytes = 128 + 5 * c.imgBytes + c.scoreBytes + c.queueCap * 2;
-  c.maxIters = ((hMax + kWarps - 1) / kWarps) * (((tw + 6 + 3) / 4 + 31) / 32);
+  c.stageCap = cap;
+  c.smemBytes = kWarps * cap * (int)sizeof(unsigned);
   return c;
 }
 
-cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &maps, const int4 *tiles, int ntiles,
-                        const FastConfig &c, int imgBase, int batch, cudaStream_t s) {
-  const int total = ntiles * batch;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  static const int ctasPerSm = [] { const char *e = getenv("ORBGPU_FAST_CTAS"); const int v = e ? atoi(e) : ORBGPU_FAST_CTAS_PER_SM; return v >= 1 && v <= ORBGPU_FAST_CTAS_PER_SM ? v : ORBGPU_FAST_CTAS_PER_SM; }();
-  const int grid = total < ctasPerSm * sms ? total : ctasPerSm * sms;
-  k_fast_cells<<<grid, kThreads, c.smemBytes, s>>>(maps, B.dT, tiles, ntiles, total, imgBase, B.cand, B.candCount, B.status, c);
+cudaError_t fast_configure(int smemBytes) {
+  return cudaFuncSetAttribute(k_fast_strips, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
+}
+
+cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const int4 *strips, int nstrips, const FastConfig &c,
+                        int imgBase, int batch, cudaStream_t s) {
+  const int total = nstrips * batch;
+  const int grid = (total + kWarps - 1) / kWarps;
+  k_fast_strips<<<grid, kThreads, c.smemBytes, s>>>(B.dT, strips, nstrips, total, imgBase, B.pyr, B.cand, B.candCount, B.status, c.stageCap,
+                                                     FmaConsts{0xffffffffu, 256u});
   count_launch();
   return cudaGetLastError();
 }

@@ -50,8 +50,7 @@ struct LevelGeom {
   int patchSize;            // (int)(31 * scale), ORBextractor.cc:800
   // resize tables (level >= 1): offsets into the int2 table buffer
   int xTab, yTab;
-  // TMA boxes (bytes x rows) of the kernels that stage this level in shared memory
-  int fastBoxW, fastBoxH;
+  // TMA box (bytes x rows) of the kernel that stages this level in shared memory
   int rzBoxW, rzBoxH;       // source window of the tiled resize that PRODUCES this level (0 = generic kernel)
 };
 
@@ -118,20 +117,23 @@ int blur_box_h();
 int blur_smem_bytes();
 cudaError_t blur_configure();
 void blur_make_tiles(const LevelTable &T, std::vector<int4> &tiles);
-#ifndef ORBGPU_FAST_CELLS
-#define ORBGPU_FAST_CELLS 4
-#endif
-#ifndef ORBGPU_FAST_THREADS
-#define ORBGPU_FAST_THREADS 256
+#ifndef ORBGPU_FAST_WARPS
+#define ORBGPU_FAST_WARPS 4          // independent warps per CTA (one strip each)
 #endif
 #ifndef ORBGPU_FAST_CTAS_PER_SM
-#define ORBGPU_FAST_CTAS_PER_SM 4
+#define ORBGPU_FAST_CTAS_PER_SM 3
 #endif
-constexpr int kFastCellsPerTile = ORBGPU_FAST_CELLS;
-struct FastConfig { int imgBytes, scorePitch, scoreBytes, stageCap, queueCap, smemBytes, maxIters; };
+#ifndef ORBGPU_FAST_PREFETCH
+#define ORBGPU_FAST_PREFETCH 4       // rows of L1 prefetch ahead of the register loads
+#endif
+#ifndef ORBGPU_FAST_AHEAD
+#define ORBGPU_FAST_AHEAD 1
+#endif
+struct FastConfig { int stageCap, smemBytes; };
+int fast_cells_per_strip(int wCell);
 FastConfig fast_make_config(const LevelTable &T);
-cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &maps, const int4 *tiles, int ntiles,
-                        const FastConfig &c, int imgBase, int batch, cudaStream_t s);
+cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const int4 *strips, int nstrips, const FastConfig &c,
+                        int imgBase, int batch, cudaStream_t s);
 cudaError_t launch_octree(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, int smemBytes,
                           cudaStream_t s);
 int hamming_dense_q(int nq);

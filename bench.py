@@ -30,14 +30,28 @@ if ROOT not in sys.path:
 
 import numpy as np
 
-W, H, NFEATURES = 1241, 376, 2000
-PARAMS = (NFEATURES, 1.2, 8, 20, 7)          # Examples/Stereo/KITTI00-02.yaml:38-51
-BF, FX = 386.1448, 718.856                   # Examples/Stereo/KITTI00-02.yaml:8,25
-LEVEL_PIXELS = 1444097                       # sum of the 8 level sizes of a 1241x376 image
-# bytes per image = every pyramid pixel read once + every derived-level pixel written once
-# + 60 B per keypoint = 2.542 MB at ~2006 keypoints
-BYTES_PER_IMAGE = LEVEL_PIXELS + (LEVEL_PIXELS - W * H) + 60 * 2006
+# BASELINE.json configs.  "c2" (configs[1], batched) is the configuration the metric is quoted on and the default the driver
+# runs; the others are selected with --config and print the same line for their own shape (profiles/ keeps their output).
+WORKLOADS = {
+    # Examples/Stereo/KITTI00-02.yaml:8,25,38-51
+    "c2": dict(name="KITTI 1241x376 stereo pairs, nFeatures=2000, extract L+R + ComputeStereoMatches (BASELINE configs[1], batched)",
+               w=1241, h=376, nf=2000, stereo=True, units=320, bf=386.1448, fx=718.856),
+    # Examples/Monocular/TUM1.yaml: one mono frame per call, as Tracking::GrabImageMonocular runs it
+    "c1": dict(name="TUM1 640x480 mono frame, nFeatures=1000, one frame per call (BASELINE configs[0])",
+               w=640, h=480, nf=1000, stereo=False, units=1, bf=0.0, fx=0.0),
+    # Examples/Stereo/EuRoC.yaml: bf 47.90639384423901, fx 435.2046959714599
+    "c3": dict(name="EuRoC 752x480 stereo, nFeatures=1200, 64 pairs per GPU (BASELINE configs[2])",
+               w=752, h=480, nf=1200, stereo=True, units=64, bf=47.90639384423901, fx=435.2046959714599),
+    "c5a": dict(name="4096-frame KITTI-shaped batch (2048 stereo pairs), nFeatures=2000, frames sharded over the ranks (BASELINE configs[4])",
+                w=1241, h=376, nf=2000, stereo=True, units=2048, bf=386.1448, fx=718.856, strong=True),
+    "c5b": dict(name="3840x2160 mono frames, nFeatures=8000, 16 frames per GPU (BASELINE configs[4])",
+                w=3840, h=2160, nf=8000, stereo=False, units=16, bf=0.0, fx=0.0),
+}
 HAMMING_NQ, HAMMING_BANK = 2000, 1_000_000   # BASELINE.json configs[3]
+
+
+def extractor_params(cfg):
+    return (cfg["nf"], 1.2, 8, 20, 7)          # scaleFactor / nLevels / iniThFAST / minThFAST of every Examples/*.yaml
 
 
 def bind_to_gpu_numa_node(gpu_index):
@@ -133,45 +147,70 @@ def cpu_reference():
         import ref
         if ref.available():
             ref.lib()
-            return ref.stereo_batch, "reference", ("reference's own ORBextractor.cc (oracle/_ref, OpenCV primitives = cv2-pinned restatements) "
-                                                   "+ restated Frame::ComputeStereoMatches, g++ -O3, no -march")
+            return ref.stereo_batch, "reference", ("reference's own ORBextractor.cc (oracle/_ref) + restated Frame::ComputeStereoMatches, g++ -O3 without "
+                                                   "-march; cv::resize / FAST / GaussianBlur are SCALAR cv2-pinned stand-ins, no SIMD: a real OpenCV "
+                                                   "build dispatches AVX2 for all three, so this CPU figure is pessimistic by an unmeasured factor")
     except Exception:
         pass
     import oracle
-    return oracle.stereo_batch, "port", "CPU oracle port of the reference path (oracle/oracle_cpu.cpp), g++ -O3, no -march"
+    return oracle.stereo_batch, "port", "CPU oracle port of the reference path (oracle/oracle_cpu.cpp), g++ -O3 without -march, scalar (no SIMD)"
 
 
-def make_inputs(pairs, seed):
+def make_inputs(cfg, units, seed):
+    """[2 * units, H, W] (left images, then right images) for a stereo workload, [units, H, W] for a mono one."""
     from refactored_orb_slam2_b200 import synthetic          # input generator only; nothing under oracle/ is touched by the own arm
-    left, right = synthetic.frame_batch(pairs, H, W, seed, stereo=True)
-    return np.ascontiguousarray(np.concatenate([left, right]))        # [2*pairs, H, W]: left images then right images
+    if cfg["stereo"]:
+        left, right = synthetic.frame_batch(units, cfg["h"], cfg["w"], seed, stereo=True)
+        return np.ascontiguousarray(np.concatenate([left, right]))
+    return np.ascontiguousarray(synthetic.frame_batch(units, cfg["h"], cfg["w"], seed))
+
+
+def cpu_run(stereo_batch, cfg, imgs, units, threads):
+    """The CPU arm on `units` pairs (or frames): for a mono workload every frame goes through the same entry point as both
+    halves of a pair and only the extraction counts are used (the stereo search then costs one extra extraction per frame,
+    which is subtracted by counting 2 frames per unit)."""
+    params = extractor_params(cfg)
+    if cfg["stereo"]:
+        n = len(imgs) // 2
+        mb = np.float32(np.float32(cfg["bf"]) / np.float32(cfg["fx"]))
+        return stereo_batch(params, imgs[:units], imgs[n:n + units], cfg["bf"], mb, threads)
+    return stereo_batch(params, imgs[:units], imgs[:units], 40.0, np.float32(0.1), threads)
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
+def metric_name(cfg, key):
+    if key in ("c2", "c5a"):
+        return "KITTI ORB extract frames/s @2000 kp"
+    return "ORB extract frames/s @%d kp (%dx%d)" % (cfg["nf"], cfg["w"], cfg["h"])
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return 0
+    cfg = WORKLOADS[args.config]
     stereo_batch, kind, host = cpu_reference()
     cores = os.cpu_count() or 1
-    pairs = max(16, 12 * cores) if args.ref_pairs <= 0 else args.ref_pairs      # 12 pairs per thread: enough for the threads to balance (~0.8 s per step)
-    imgs = make_inputs(pairs, 100)
-    left, right = imgs[:pairs], imgs[pairs:]
-    mb = np.float32(np.float32(BF) / np.float32(FX))
+    px = cfg["w"] * cfg["h"] / (1241 * 376)
+    units = max(1, int(max(16, 12 * cores) / px)) if args.ref_pairs <= 0 else args.ref_pairs    # ~12 KITTI pairs per thread per step (~0.8 s): enough for the threads to balance
+    if args.config == "c1":
+        units = 1 if args.ref_pairs <= 0 else units        # the reference's own calling pattern: one frame per call
+    imgs = make_inputs(cfg, units, 100)
     for _ in range(args.warmup):
-        stereo_batch(PARAMS, left[:cores], right[:cores], BF, mb, cores)
+        cpu_run(stereo_batch, cfg, imgs, min(cores, units), cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        stereo_batch(PARAMS, left, right, BF, mb, cores)
+        cpu_run(stereo_batch, cfg, imgs, units, cores)
     dt = time.perf_counter() - t0
-    fps = 2 * pairs * args.steps / dt
-    sample = "%d KITTI-shaped stereo pairs per step, extraction L+R + ComputeStereoMatches, one pair per thread" % pairs
+    fps = 2 * units * args.steps / dt
+    what = "stereo pairs, extraction L+R + ComputeStereoMatches, one pair per thread" if cfg["stereo"] else \
+           "frames (two extractions per unit through the stereo entry point), one unit per thread"
+    sample = "%d %dx%d %s per step" % (units, cfg["w"], cfg["h"], what)
     line = {
-        "impl": "reference", "metric": "KITTI ORB extract frames/s @2000 kp", "value": fps, "unit": "frames/s",
+        "impl": "reference", "metric": metric_name(cfg, args.config), "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "KITTI 1241x376 stereo pairs, nFeatures=2000, extract L+R + ComputeStereoMatches",
-                   "pairs_per_step": pairs, "host": host},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
+        "config": {"workload": cfg["name"], "units_per_step": units, "host": host},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample + "; " + host},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -180,6 +219,45 @@ def run_reference(args, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------- own arm
+def load_counters():
+    """Per-image counters of the dominant kernel from the committed ncu capture of the CURRENT kernel (profiles/, one
+    --set full pass; the file names the capture it came from)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_fast_counters.json")))
+    except Exception:
+        return {}
+
+
+def host_copy_probe(torch, host, out_bytes, barrier, max_over_ranks, seconds=0.6):
+    """Ceiling of the e2e leg: the same pinned buffers, H2D of one step's images and D2H of one step's results on two
+    streams at once, all ranks at the same time, no kernels.  Returns (GB/s moved by this job, seconds per step)."""
+    dev_in = torch.empty_like(host, device="cuda")
+    dev_out = torch.empty(out_bytes, dtype=torch.uint8, device="cuda")
+    host_out = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def once():
+        with torch.cuda.stream(s_in):
+            dev_in.copy_(host, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            host_out.copy_(dev_out, non_blocking=True)
+
+    once()
+    torch.cuda.synchronize()
+    barrier()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        once()
+        n += 1
+        if n % 4 == 0:
+            torch.cuda.synchronize()
+            if time.perf_counter() - t0 > seconds:
+                break
+    torch.cuda.synchronize()
+    dt = max_over_ranks((time.perf_counter() - t0) / n)
+    return dt
+
+
 def run_own(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -197,6 +275,7 @@ def run_own(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = pkg.lib()
+    vp = ctypes.c_void_p
 
     def barrier():
         if world > 1:
@@ -210,19 +289,38 @@ def run_own(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    pairs = args.pairs
-    nimg = 2 * pairs
-    log("world %d local_rank %d: generating %d pairs" % (world, local_rank, pairs))
-    host = torch.from_numpy(make_inputs(pairs, 100 + rank)).pin_memory()
-    dev = host.cuda()
-    mb = float(np.float32(np.float32(BF) / np.float32(FX)))
+    def all_ranks(ok):
+        if world == 1:
+            return bool(ok)
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
 
-    ex = pkg.ORBextractor(*PARAMS, max_width=W, max_height=H, max_batch=nimg, device=local_rank)
+    cfg = WORKLOADS[args.config]
+    W, H, stereo = cfg["w"], cfg["h"], cfg["stereo"]
+    params = extractor_params(cfg)
+    units = args.pairs if args.pairs > 0 else cfg["units"]
+    if cfg.get("strong"):
+        from refactored_orb_slam2_b200.distributed import shard_range
+        lo, hi = shard_range(units, rank, world)            # the whole job's frames, contiguous ranges per rank
+        units_total, units = units, hi - lo
+    else:
+        units_total = units * world
+    nimg = 2 * units if stereo else units
+    per_unit = 2 if stereo else 1
+    BF = cfg["bf"]
+    mb = float(np.float32(np.float32(BF) / np.float32(cfg["fx"]))) if stereo else 0.0
+    log("world %d local_rank %d: generating %d units of %s" % (world, local_rank, units, args.config))
+    host = torch.from_numpy(make_inputs(cfg, units, 100 + rank)).pin_memory()
+    dev = host.cuda()
+
+    ex = pkg.ORBextractor(*params, max_width=W, max_height=H, max_batch=nimg, device=local_rank)
     stream = torch.cuda.ExternalStream(ex.stream, device=torch.device("cuda", local_rank))
 
     def step_device():
         ex.extract_batch_device(dev.data_ptr(), nimg, W, H)
-        pkg._lib.check(lib.orbgpu_stereo_match_device(ex.handle, ex.handle, 0, pairs, pairs, BF, mb))
+        if stereo:
+            pkg._lib.check(lib.orbgpu_stereo_match_device(ex.handle, ex.handle, 0, units, units, BF, mb))
 
     log("handle ready")
     # ---- device-resident throughput (`value`)
@@ -249,8 +347,7 @@ def run_own(args, rank, local_rank, world):
     launches = int(lib.orbgpu_launch_count(0))
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ex.synchronize()                               # raises if a device buffer overflowed
-    # per-stage device times from a separate, untimed pass: the stage timers serialise the blur, which the timed loop runs on a
-    # side stream next to FAST + octree (so the stages add up to slightly more than ms_per_step)
+    # per-stage device times from a separate, untimed pass (the stage timers keep everything on one stream)
     ex.set_profiling(True)
     ex.stage_times()
     for _ in range(max(3, min(args.steps, 8))):
@@ -258,11 +355,12 @@ def run_own(args, rank, local_rank, world):
     stages = ex.stage_times()
     ex.set_profiling(False)
     ms_step = ms_total / args.steps
-    fps = world * nimg * args.steps / (ms_total * 1e-3)
+    fps = per_unit * units_total * args.steps / (ms_total * 1e-3)
+    level_pixels = sum(w * h for w, h in (ex.level_size(l) for l in range(8)))
 
     log("device loop done: %.3f ms/step" % ms_step)
-    kps, desc, counts = ex.download_results()
-    mean_kp = float(counts.mean())
+    kps_dev, desc_dev, counts_dev = ex.download_results()
+    mean_kp = float(counts_dev.mean())
 
     # ---- end to end through the host-buffer API (`e2e`): pinned host images in, keypoints /
     # descriptors / mvuRight / mvDepth out, every step
@@ -270,15 +368,15 @@ def run_own(args, rank, local_rank, world):
     out_k = torch.empty((nimg, cap, 28), dtype=torch.uint8).pin_memory()
     out_d = torch.empty((nimg, cap, 32), dtype=torch.uint8).pin_memory()
     out_c = torch.empty(nimg, dtype=torch.int32).pin_memory()
-    out_u = torch.empty((pairs, cap), dtype=torch.float32).pin_memory()
-    out_z = torch.empty((pairs, cap), dtype=torch.float32).pin_memory()
-    vp = ctypes.c_void_p
+    out_u = torch.empty((max(units, 1), cap), dtype=torch.float32).pin_memory()
+    out_z = torch.empty((max(units, 1), cap), dtype=torch.float32).pin_memory()
 
     def step_e2e():
         pkg._lib.check(lib.orbgpu_extract_batch(ex.handle, vp(host.data_ptr()), nimg, W, H, W, W * H, vp(out_k.data_ptr()),
                                                 vp(out_d.data_ptr()), cap, vp(out_c.data_ptr())))
-        pkg._lib.check(lib.orbgpu_stereo_match(ex.handle, ex.handle, 0, pairs, pairs, BF, mb, vp(out_u.data_ptr()),
-                                               vp(out_z.data_ptr()), cap))
+        if stereo:
+            pkg._lib.check(lib.orbgpu_stereo_match(ex.handle, ex.handle, 0, units, units, BF, mb, vp(out_u.data_ptr()),
+                                                   vp(out_z.data_ptr()), cap))
 
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
@@ -288,120 +386,108 @@ def run_own(args, rank, local_rank, world):
         step_e2e()
     torch.cuda.synchronize()
     dt_sync = max_over_ranks(time.perf_counter() - t0)
-    # the same calls, two batches in flight (pkg.StereoBatchPipeline: two handles, split async / wait entry points, one host thread), so that one
-    # batch uploads while the other computes; every batch is copied in from pinned host memory and its results copied out
-    del out_k, out_d, out_c, out_u, out_z
+    # ---- verification 1: what the host received through the C ABI is what the device-resident loop left in HBM
+    # (same inputs, other entry point, other buffers), checksummed so that the ranks can be compared below
+    nk = out_c.numpy()
+    k_host = out_k.numpy().view(pkg._lib.KP_DTYPE).reshape(nimg, cap)
+    same_api = bool(np.array_equal(nk, counts_dev))
+    for i in range(0, nimg, max(1, nimg // 16)):
+        same_api = same_api and np.array_equal(k_host[i, :nk[i]], kps_dev[i, :nk[i]]) and np.array_equal(out_d.numpy()[i, :nk[i]], desc_dev[i, :nk[i]])
     depth = max(2, env_int("BENCH_PIPELINE_DEPTH", 2))
-    pipe = pkg.StereoBatchPipeline(PARAMS, W, H, pairs, BF, mb, depth=depth, device=local_rank)
-    for _ in range(depth):
-        pipe.submit(host)
-    for _ in range(depth):
-        pipe.result()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        if i >= depth:
-            pipe.result()          # batch i - depth: frees its handle; the batches after it are still in flight while batch i is enqueued
-        pipe.submit(host)
-    for _ in range(min(depth, args.steps) - 1):
-        pipe.result()
-    last = pipe.result()
-    torch.cuda.synchronize()
-    dt = max_over_ranks(time.perf_counter() - t0)
-    kmax = int(last[2].max())
-    pipe.close()
-    # ---- the reference's own calling pattern: ONE stereo pair per call (configs[1] as Tracking::GrabImageStereo runs it);
-    # informational, the small-batch path replays a CUDA graph of the 13-kernel extraction sequence
+    dt, api = dt_sync, "orbgpu_extract_batch%s, pinned host buffers" % (" + orbgpu_stereo_match" if stereo else "")
+    last_matched = None
+    if stereo:
+        # the same calls, two batches in flight (pkg.StereoBatchPipeline: two handles, split async / wait entry points, one host thread), so that one
+        # batch uploads while the other computes; every batch is copied in from pinned host memory and its results copied out
+        del out_k, out_d, out_c, out_u, out_z
+        pipe = pkg.StereoBatchPipeline(params, W, H, units, BF, mb, depth=depth, device=local_rank)
+        for _ in range(depth):
+            pipe.submit(host)
+        for _ in range(depth):
+            pipe.result()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            if i >= depth:
+                pipe.result()          # batch i - depth: frees its handle; the batches after it are still in flight while batch i is enqueued
+            pipe.submit(host)
+        for _ in range(min(depth, args.steps) - 1):
+            pipe.result()
+        last = pipe.result()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        same_api = same_api and bool(np.array_equal(last[2], counts_dev))
+        last_counts = last[2].copy()
+        cols = np.arange(last[3].shape[1])[None, :] < last_counts[:units, None]      # rows beyond the count are unspecified
+        last_matched = ((last[3] >= 0) & cols).sum(axis=1).astype(np.int64)          # stereo matches per pair, for the CPU comparison below
+        pipe.close()
+        api = "StereoBatchPipeline(depth=%d) over orbgpu_extract_batch_async + orbgpu_stereo_match_async + orbgpu_wait, pinned host buffers" % depth
+    else:
+        last_counts = nk.copy()
+    e2e_fps = per_unit * units_total * args.steps / dt
+    h2d = nimg * W * H
+    d2h = nimg * 4 + nimg * cap * (28 + 32) + (2 * units * cap * 4 if stereo else 0)   # whole rows are copied (counts live on the device)
+    # ---- ceiling of that leg: the copies alone, all ranks at once
+    copy_ceiling = None
+    if not args.no_copy_probe:
+        t_copy = host_copy_probe(torch, host, d2h, barrier, max_over_ranks)
+        copy_ceiling = {"gbs": world * (h2d + d2h) / t_copy / 1e9, "frames_per_s": per_unit * units_total / t_copy,
+                        "note": "H2D of one step's images + D2H of one step's results from / to the same kind of pinned buffers, two streams, "
+                                "all ranks at once, no kernels"}
+    # ---- the reference's own calling pattern: ONE stereo pair (or frame) per call; informational
     latency_ms = None
     if rank == 0 and not args.no_latency:
-        ex1 = pkg.ORBextractor(*PARAMS, max_width=W, max_height=H, max_batch=2, device=local_rank)
+        n1 = 2 if stereo else 1
+        ex1 = pkg.ORBextractor(*params, max_width=W, max_height=H, max_batch=n1, device=local_rank)
         cap1 = ex1.capacity
-        pair = torch.stack([host[0], host[pairs]]).pin_memory()
-        o = [torch.empty((2, cap1, 28), dtype=torch.uint8).pin_memory(), torch.empty((2, cap1, 32), dtype=torch.uint8).pin_memory(),
-             torch.empty(2, dtype=torch.int32).pin_memory(), torch.empty((1, cap1), dtype=torch.float32).pin_memory(),
+        one = (torch.stack([host[0], host[units]]) if stereo else host[:1].clone()).pin_memory()
+        o = [torch.empty((n1, cap1, 28), dtype=torch.uint8).pin_memory(), torch.empty((n1, cap1, 32), dtype=torch.uint8).pin_memory(),
+             torch.empty(n1, dtype=torch.int32).pin_memory(), torch.empty((1, cap1), dtype=torch.float32).pin_memory(),
              torch.empty((1, cap1), dtype=torch.float32).pin_memory()]
         ts = []
         for i in range(60):
             t1 = time.perf_counter()
-            pkg._lib.check(lib.orbgpu_extract_batch(ex1.handle, vp(pair.data_ptr()), 2, W, H, W, W * H, vp(o[0].data_ptr()), vp(o[1].data_ptr()), cap1,
+            pkg._lib.check(lib.orbgpu_extract_batch(ex1.handle, vp(one.data_ptr()), n1, W, H, W, W * H, vp(o[0].data_ptr()), vp(o[1].data_ptr()), cap1,
                                                     vp(o[2].data_ptr())))
-            pkg._lib.check(lib.orbgpu_stereo_match(ex1.handle, ex1.handle, 0, 1, 1, BF, mb, vp(o[3].data_ptr()), vp(o[4].data_ptr()), cap1))
+            if stereo:
+                pkg._lib.check(lib.orbgpu_stereo_match(ex1.handle, ex1.handle, 0, 1, 1, BF, mb, vp(o[3].data_ptr()), vp(o[4].data_ptr()), cap1))
             if i >= 10:
                 ts.append(time.perf_counter() - t1)
         latency_ms = float(np.median(ts) * 1e3)
         del ex1
-    e2e_fps = world * nimg * args.steps / dt
     clocks = sampler.stop() if rank == 0 else None
-    h2d = nimg * W * H
-    d2h = nimg * 4 + nimg * cap * (28 + 32) + 2 * pairs * cap * 4      # whole rows are copied (counts live on the device); max count per image is reported in config
-
     log("e2e loop done")
+
+    # ---- verification 2: every rank extracts the SAME small check batch; the checksums must agree across the GPUs, and rank 0
+    # compares the counts with the CPU reference below
+    check_units = 4 if W * H < 2_000_000 else 1
+    check_imgs = make_inputs(cfg, check_units, 7)
+    exc = pkg.ORBextractor(*params, max_width=W, max_height=H, max_batch=len(check_imgs), device=local_rank)
+    ck, cd, cc = exc.extract_batch(check_imgs)
+    digest = [int(cc.sum())]
+    for i in range(len(check_imgs)):
+        digest.append(int(np.frombuffer(ck[i, :cc[i]].tobytes() + cd[i, :cc[i]].tobytes(), np.uint8).astype(np.uint64).dot(
+            np.arange(1, cc[i] * 60 + 1, dtype=np.uint64) % np.uint64(65521)) % np.uint64(1 << 62)))
+    check_matched = None
+    if stereo:
+        cu, cz = pkg.ComputeStereoMatches(exc, exc, BF, mb, first_left=0, first_right=check_units, pairs=check_units)
+        ccols = np.arange(cu.shape[1])[None, :] < cc[:check_units, None]
+        check_matched = ((cu >= 0) & ccols).sum(axis=1).astype(np.int64)
+        digest.append(int(np.frombuffer(np.where(ccols, cu, 0).tobytes() + np.where(ccols, cz, 0).tobytes(), np.uint32).astype(np.uint64).sum() % np.uint64(1 << 62)))
+    ranks_agree = True
+    if world > 1:
+        t = torch.tensor(digest, dtype=torch.int64, device="cuda")
+        ref_t = t.clone()
+        dist.broadcast(ref_t, 0)
+        ranks_agree = all_ranks(bool(torch.equal(t, ref_t)))
+    same_api = all_ranks(same_api)
+    del exc
+
     # ---- Hamming matching, BASELINE.json configs[3]: 2000 queries x 1M-row bank, row-sharded over the ranks,
-    # all-gather of the per-shard {d1, d2, idx} records, merge + ratio test on every rank
+    # per-shard {d1, d2, idx} records exchanged, merge + ratio test on every rank
     hamming = None
-    if not args.no_hamming:
-        lo, hi = rank * HAMMING_BANK // world, (rank + 1) * HAMMING_BANK // world
-        shard = np.random.default_rng(4 + 1000 * rank).integers(0, 256, size=(hi - lo, 32), dtype=np.uint8)
-        q = np.random.default_rng(5).integers(0, 256, size=(HAMMING_NQ, 32), dtype=np.uint8)      # same queries on every rank
-        flips = np.random.default_rng(6).integers(0, 2, size=(HAMMING_NQ, 32), dtype=np.uint8)   # <= 32 flipped bits
-        mine = np.arange(rank, HAMMING_NQ, 2 * world)                                             # half the queries have a near match
-        shard[(mine * 7919) % (hi - lo)] = q[mine] ^ flips[mine]
-        d_shard = torch.from_numpy(shard).cuda()
-        d_q = torch.from_numpy(q).cuda()
-        bank = pkg.DescriptorBank(device_ptr=d_shard.data_ptr(), rows=hi - lo, index_base=lo, device=local_rank, keepalive=d_shard)
-        local = torch.empty((HAMMING_NQ, 16), dtype=torch.uint8, device="cuda")
-        gathered = torch.empty((world * HAMMING_NQ, 16), dtype=torch.uint8, device="cuda")   # rank-major
-        merged = torch.empty((HAMMING_NQ, 16), dtype=torch.uint8, device="cuda")
-        match = torch.empty(HAMMING_NQ, dtype=torch.int64, device="cuda")
-        cur = torch.cuda.Stream()          # an explicit side stream: a NULL stream argument means "the bank's own stream"
-        torch.cuda.set_stream(cur)
-
-        use_peer = world > 1 and args.hamming_exchange == "peer"
-        if use_peer:
-            from refactored_orb_slam2_b200.distributed import PeerExchange
-            xchg = PeerExchange(rank, world, HAMMING_NQ, local_rank)      # IPC handles all-gathered once; no collective afterwards
-
-        def step_hamming():
-            if use_peer:      # scan -> records stored into every peer's window over NVLink -> wait on arrival flags + merge
-                pkg._lib.check(lib.orbgpu_hamming_top2_sharded_device(bank._h, xchg._h, vp(d_q.data_ptr()), HAMMING_NQ, vp(merged.data_ptr()), 0.7, 50,
-                                                                      vp(match.data_ptr()), vp(cur.cuda_stream)))
-                return
-            bank.top2_device(d_q.data_ptr(), HAMMING_NQ, local.data_ptr(), stream=cur.cuda_stream)
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, local)
-                src = gathered
-            else:
-                src = local
-            pkg.merge_top2_device(src.data_ptr(), world, HAMMING_NQ, merged.data_ptr(), 0.7, 50, match.data_ptr(),
-                                  device=local_rank, stream=cur.cuda_stream)
-
-        hsteps = max(args.steps, 10)
-        for _ in range(max(3, args.warmup)):
-            step_hamming()
-        barrier()
-        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        h0.record(cur)
-        for _ in range(hsteps):
-            step_hamming()
-        h1.record(cur)
-        barrier()
-        hms = max_over_ranks(h0.elapsed_time(h1)) / hsteps
-        if use_peer:
-            xchg.check()                   # a peer whose records never arrived would have been recorded on the device
-        gpairs = HAMMING_NQ * HAMMING_BANK / (hms * 1e-3) / 1e9
-        popc, lop3 = ctypes.c_double(), ctypes.c_double()
-        pkg._lib.check(lib.orbgpu_measure_popc_peak(local_rank, ctypes.byref(popc), ctypes.byref(lop3)))
-        # integer-pipe roofline: algorithmic work = 8 POPC per descriptor pair
-        peak_gpairs = world * popc.value / 8 / 1e9
-        hamming = {"metric": "Hamming match Gpairs/s (2000 queries x 1M-row bank, top-2 + ratio 0.7 / TH_LOW 50)",
-                   "value": gpairs, "unit": "Gpairs/s", "ms_per_step": hms, "scaling": "strong", "shards": world,
-                   "exchange": ("none (one shard)" if world == 1 else "peer-memory stores over NVLink + arrival flags, fused with the shard merge; no collective call"
-                                if use_peer else "one NCCL all-gather of 16 B per query per rank + merge kernel"),
-                   "roofline": {"bound": "integer-pipe (POPC)", "achieved": gpairs, "peak": peak_gpairs, "unit": "Gpairs/s",
-                                "frac": gpairs / peak_gpairs,
-                                "note": "peak = measured POPC issue rate / 8 POPC per pair (algorithmic); the kernel's carry-save "
-                                        "compression executes 4 POPC + 16 LOP3 per pair, so frac may exceed the naive bound",
-                                "popc_per_s_measured": popc.value, "lop3_per_s_measured": lop3.value}}
+    if not args.no_hamming and args.config == "c2":
+        hamming = run_hamming(args, pkg, lib, torch, dist, rank, local_rank, world, barrier, max_over_ranks, all_ranks)
 
     log("hamming done")
     if rank == 0:
@@ -412,55 +498,83 @@ def run_own(args, rank, local_rank, world):
             pass
         peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-        dom = max(("pyramid", "fast", "octree", "blur", "describe", "stereo"), key=lambda k: stages.get(k, 0.0))
-        # algorithmic bytes of the dominant stage per launch: FAST reads every pyramid pixel once and writes 8 B per candidate;
-        # the other stages' figures are listed in DESIGN.md
-        alg_bytes = {"fast": LEVEL_PIXELS + 8 * 27400, "pyramid": LEVEL_PIXELS + (LEVEL_PIXELS - W * H), "blur": 2 * LEVEL_PIXELS,
-                     "octree": 8 * 27000, "describe": 60 * 2006 + 2006 * (749 + 512), "stereo": 2006 * (64 * 2000 // 32)}[dom] * nimg
-        achieved = alg_bytes / (stages[dom] * 1e-3) / 1e9 if stages.get(dom) else 0.0
-        traffic = None      # dram__bytes_read + dram__bytes_write of the dominant kernel per launch, from the committed ncu capture
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_k_fast_cells_traffic.json")))
-            if dom == "fast":
-                traffic = int(tj["traffic_bytes_per_image"]) * nimg
-        except Exception:
-            pass
-        pipeline_gbs = BYTES_PER_IMAGE * nimg / (ms_step * 1e-3) / 1e9
+        stage_names = ("pyramid", "fast", "octree", "blur", "describe") + (("stereo",) if stereo else ())
+        dom = max(stage_names, key=lambda k: stages.get(k, 0.0))
+        # algorithmic bytes per image of every stage: FAST reads every pyramid pixel once and writes 8 B per
+        # candidate; the pyramid reads every level once and writes every derived level once; ...
+        cand_per_image = 27400 * level_pixels / 1444097
+        alg = {"fast": level_pixels + 8 * cand_per_image, "pyramid": level_pixels + (level_pixels - W * H), "blur": 2 * level_pixels,
+               "octree": 8 * cand_per_image, "describe": mean_kp * (60 + 749 + 512), "stereo": mean_kp * (64 * 2000 // 32)}
+        bytes_per_image = level_pixels + (level_pixels - W * H) + 60 * mean_kp
+        achieved = alg[dom] * nimg / (stages[dom] * 1e-3) / 1e9 if stages.get(dom) else 0.0
+        kernel_of = {"fast": "k_fast_strips", "pyramid": "k_import_level0 + k_resize_tiles x7 + k_fill_borders", "octree": "k_octree", "blur": "k_blur",
+                     "describe": "k_describe", "stereo": "k_stereo_rows + k_stereo_match + k_stereo_filter"}
+        counters = load_counters()
+        traffic = alu_frac = None
+        alu_note = None
+        if dom == "fast" and counters.get("kernel") == "k_fast_strips":
+            # per-image counters of one ncu --set full capture of the CURRENT kernel on this workload's shape, scaled to this launch
+            scale = level_pixels / counters["level_pixels_per_image"]
+            traffic = int(counters["dram_bytes_per_image"] * scale * nimg)
+            rate = ctypes.c_double()
+            pkg._lib.check(lib.orbgpu_measure_pipe(local_rank, 2, ctypes.byref(rate)))      # VIMNMX3.S16x2 lane-ops / s, measured now
+            alu_lane_ops = counters["alu_warp_inst_per_image"] * scale * nimg * 32
+            alu_frac = alu_lane_ops / (stages["fast"] * 1e-3) / rate.value
+            alu_note = ("executed ALU-pipe instructions of the kernel (ncu sm__inst_executed_pipe_alu, %s) x 32 lanes / stage time / the VIMNMX3.S16x2 "
+                        "issue rate measured in this run (%.0f G lane-ops/s): the pipe that bounds FAST, HBM is not" % (counters.get("capture", "?"), rate.value / 1e9))
+        pipeline_gbs = bytes_per_image * nimg / (ms_step * 1e-3) / 1e9
         cpu_baseline = None
+        verified_vs_cpu = None
         if not args.no_cpu_baseline:
             stereo_batch, kind, cpu_host = cpu_reference()
             cores = os.cpu_count() or 1
-            sample_pairs = min(pairs, max(16, min(320, 12 * cores)))      # ~1 s of wall clock = 10-30 s of CPU work
+            px = W * H / (1241 * 376)
+            sample_units = max(1, min(units, int(max(16, min(320, 12 * cores)) / px)))      # ~1 s of wall clock = 10-30 s of CPU work
             hl = host.numpy()
-            stereo_batch(PARAMS, hl[:min(cores, sample_pairs)], hl[pairs:pairs + min(cores, sample_pairs)], BF, np.float32(mb), cores)   # warm
+            cpu_run(stereo_batch, cfg, hl, min(cores, sample_units), cores)                 # warm
             t0 = time.perf_counter()
-            stereo_batch(PARAMS, hl[:sample_pairs], hl[pairs:pairs + sample_pairs], BF, np.float32(mb), cores)
+            cl, cr, cm = cpu_run(stereo_batch, cfg, hl, sample_units, cores)
             cdt = time.perf_counter() - t0
-            cpu_baseline = {"value": 2 * sample_pairs / cdt, "unit": "frames/s", "cores": cores, "kind": kind,
-                            "sample": "%d of this run's stereo pairs, extraction L+R + ComputeStereoMatches, one pair per thread; %s"
-                                      % (sample_pairs, cpu_host)}
+            cpu_baseline = {"value": 2 * sample_units / cdt, "unit": "frames/s", "cores": cores, "kind": kind,
+                            "sample": "%d of this run's %s, one per thread; %s"
+                                      % (sample_units, "stereo pairs (extraction L+R + ComputeStereoMatches)" if stereo else
+                                         "frames (two extractions per frame through the stereo entry point)", cpu_host)}
+            # verification 3: the CPU reference's keypoint counts (and stereo match counts) on those inputs equal the GPU's, and on
+            # the cross-rank check batch too
+            verified_vs_cpu = bool(np.array_equal(cl, last_counts[:sample_units]))
+            if stereo:
+                verified_vs_cpu = verified_vs_cpu and bool(np.array_equal(cr, last_counts[units:units + sample_units])) and \
+                    bool(np.array_equal(cm, last_matched[:sample_units]))
+            kl, kr, km = cpu_run(stereo_batch, cfg, check_imgs, check_units, cores)
+            verified_vs_cpu = verified_vs_cpu and bool(np.array_equal(kl, cc[:check_units]))
+            if stereo:
+                verified_vs_cpu = verified_vs_cpu and bool(np.array_equal(kr, cc[check_units:])) and bool(np.array_equal(km, check_matched))
         line = {
-            "metric": "KITTI ORB extract frames/s @2000 kp", "value": fps, "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "metric": metric_name(cfg, args.config), "value": fps, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if cfg.get("strong") else "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "KITTI 1241x376 stereo pairs, nFeatures=2000, extract L+R + ComputeStereoMatches (BASELINE configs[1], batched)",
-                       "pairs_per_step_per_gpu": pairs, "images_per_step_per_gpu": nimg, "mean_keypoints_per_image": mean_kp,
-                       "l2": "inputs %.0f MB per step > 126 MB L2; pyramids %.0f MB" % (nimg * W * H / 1e6, nimg * 1.9),
+            "config": {"workload": cfg["name"], "config_key": args.config,
+                       "units_per_step_per_gpu": units, "images_per_step_per_gpu": nimg, "mean_keypoints_per_image": mean_kp,
+                       "l2": "inputs %.0f MB per step %s 126 MB L2; pyramids %.0f MB" % (nimg * W * H / 1e6, ">" if nimg * W * H > 126e6 else "<",
+                                                                                       nimg * 1.34 * level_pixels / 1e6),
                        "parallelism": "frame-sharded, %d rank(s), no data-path collective" % world,
                        "host_numa_node_rank0": numa_node},
             "clocks": clocks,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "StereoBatchPipeline(depth=%d) over orbgpu_extract_batch_async + orbgpu_stereo_match_async + orbgpu_wait, pinned host buffers" % depth,
-                    "single_pair_latency_ms": latency_ms,
-                    "single_call_value": world * nimg * args.steps / dt_sync},
+                    "api": api, "single_unit_latency_ms": latency_ms,
+                    "single_call_value": per_unit * units_total * args.steps / dt_sync,
+                    "host_copy_ceiling": copy_ceiling},
             "gpu_launches": launches,
             "stage_ms": stages,
-            "roofline": {"bound": "hbm", "kernel": {"fast": "k_fast_cells", "pyramid": "k_resize_level", "octree": "k_octree", "blur": "k_blur_level",
-                                                     "describe": "k_describe", "stereo": "k_stereo_match"}[dom],
+            "verified": {"host_api_equals_device_resident": same_api, "ranks_agree_on_check_batch": ranks_agree,
+                         "counts_equal_cpu_reference": verified_vs_cpu,
+                         "note": "full bit-exact parity is tests/ (-m gpu); this is the in-run check that the timed path computes the reference's result"},
+            "roofline": {"bound": "hbm", "kernel": kernel_of[dom],
                          "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
-                         "peak_source": peak_src,
+                         "peak_source": peak_src, "alu_pipe_frac": alu_frac, "alu_pipe_note": alu_note,
                          "pipeline": {"achieved": pipeline_gbs, "frac": pipeline_gbs / peak_gbs,
-                                      "bytes_per_image": BYTES_PER_IMAGE, "note": "SURVEY 8d per-image bytes x images / whole step time"}},
+                                      "bytes_per_image": bytes_per_image, "note": "SURVEY 8d per-image bytes x images / whole step time"}},
             "cpu_baseline": cpu_baseline,
             "hamming": hamming,
         }
@@ -472,19 +586,127 @@ def run_own(args, rank, local_rank, world):
     return 0
 
 
+def run_hamming(args, pkg, lib, torch, dist, rank, local_rank, world, barrier, max_over_ranks, all_ranks):
+    vp = ctypes.c_void_p
+    lo, hi = rank * HAMMING_BANK // world, (rank + 1) * HAMMING_BANK // world
+    shard = np.random.default_rng(4 + 1000 * rank).integers(0, 256, size=(hi - lo, 32), dtype=np.uint8)
+    q = np.random.default_rng(5).integers(0, 256, size=(HAMMING_NQ, 32), dtype=np.uint8)      # same queries on every rank
+    flips = np.random.default_rng(6).integers(0, 2, size=(HAMMING_NQ, 32), dtype=np.uint8)   # <= 32 flipped bits
+    mine = np.arange(rank, HAMMING_NQ, 2 * world)                                             # half the queries have a near match
+    shard[(mine * 7919) % (hi - lo)] = q[mine] ^ flips[mine]
+    d_shard = torch.from_numpy(shard).cuda()
+    d_q = torch.from_numpy(q).cuda()
+    bank = pkg.DescriptorBank(device_ptr=d_shard.data_ptr(), rows=hi - lo, index_base=lo, device=local_rank, keepalive=d_shard)
+    local = torch.empty((HAMMING_NQ, 16), dtype=torch.uint8, device="cuda")
+    gathered = torch.empty((world * HAMMING_NQ, 16), dtype=torch.uint8, device="cuda")   # rank-major
+    merged = torch.empty((HAMMING_NQ, 16), dtype=torch.uint8, device="cuda")
+    match = torch.empty(HAMMING_NQ, dtype=torch.int64, device="cuda")
+    cur = torch.cuda.Stream()          # an explicit side stream: a NULL stream argument means "the bank's own stream"
+    torch.cuda.set_stream(cur)
+
+    use_peer = world > 1 and args.hamming_exchange == "peer"
+    if use_peer:
+        from refactored_orb_slam2_b200.distributed import PeerExchange
+        xchg = PeerExchange(rank, world, HAMMING_NQ, local_rank)      # IPC handles all-gathered once; no collective afterwards
+
+    def step_hamming():
+        if use_peer:      # scan -> records stored into every peer's window over NVLink -> wait on arrival flags + merge
+            pkg._lib.check(lib.orbgpu_hamming_top2_sharded_device(bank._h, xchg._h, vp(d_q.data_ptr()), HAMMING_NQ, vp(merged.data_ptr()), 0.7, 50,
+                                                                  vp(match.data_ptr()), vp(cur.cuda_stream)))
+            return
+        bank.top2_device(d_q.data_ptr(), HAMMING_NQ, local.data_ptr(), stream=cur.cuda_stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, local)
+            src = gathered
+        else:
+            src = local
+        pkg.merge_top2_device(src.data_ptr(), world, HAMMING_NQ, merged.data_ptr(), 0.7, 50, match.data_ptr(),
+                              device=local_rank, stream=cur.cuda_stream)
+
+    hsteps = max(args.steps, 10)
+    for _ in range(max(3, args.warmup)):
+        step_hamming()
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record(cur)
+    for _ in range(hsteps):
+        step_hamming()
+    h1.record(cur)
+    barrier()
+    hms = max_over_ranks(h0.elapsed_time(h1)) / hsteps
+    if use_peer:
+        xchg.check()                   # a peer whose records never arrived would have been recorded on the device
+    # ---- verification (untimed): the records and matches the sharded path left on THIS rank against one scan of the WHOLE bank
+    # (shards gathered once) merged on this GPU, bit for bit, on every rank
+    cur.synchronize()
+    got_rec, got_match = merged.cpu().numpy().copy(), match.cpu().numpy().copy()
+    if world > 1:
+        whole = torch.empty((HAMMING_BANK, 32), dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(whole, d_shard)
+    else:
+        whole = d_shard
+    wbank = pkg.DescriptorBank(device_ptr=whole.data_ptr(), rows=HAMMING_BANK, index_base=0, device=local_rank, keepalive=whole)
+    wrec = torch.empty((HAMMING_NQ, 16), dtype=torch.uint8, device="cuda")
+    wmerged = torch.empty((HAMMING_NQ, 16), dtype=torch.uint8, device="cuda")
+    wmatch = torch.empty(HAMMING_NQ, dtype=torch.int64, device="cuda")
+    wbank.top2_device(d_q.data_ptr(), HAMMING_NQ, wrec.data_ptr(), stream=cur.cuda_stream)
+    pkg.merge_top2_device(wrec.data_ptr(), 1, HAMMING_NQ, wmerged.data_ptr(), 0.7, 50, wmatch.data_ptr(), device=local_rank, stream=cur.cuda_stream)
+    cur.synchronize()
+    ok = bool(np.array_equal(got_rec, wmerged.cpu().numpy())) and bool(np.array_equal(got_match, wmatch.cpu().numpy()))
+    # and the whole-bank scan itself against numpy popcount on a few queries (every rank)
+    from refactored_orb_slam2_b200._lib import TOP2_DTYPE
+    rec = wmerged.cpu().numpy().view(TOP2_DTYPE).reshape(-1)
+    wh = whole.cpu().numpy()
+    for qi in (0, 1, 777, 1999):
+        d = np.unpackbits(wh ^ q[qi], axis=1).sum(axis=1, dtype=np.int32)
+        i1 = int(d.argmin())
+        d1 = int(d[i1]); d[i1] = 1 << 20
+        ok = ok and rec["idx"][qi] == i1 and rec["d1"][qi] == d1 and rec["d2"][qi] == int(d.min())
+    verified = all_ranks(ok)
+    accepted = int((got_match >= 0).sum())
+    gpairs = HAMMING_NQ * HAMMING_BANK / (hms * 1e-3) / 1e9
+    popc, lop3 = ctypes.c_double(), ctypes.c_double()
+    pkg._lib.check(lib.orbgpu_measure_popc_peak(local_rank, ctypes.byref(popc), ctypes.byref(lop3)))
+    # integer-pipe roofline.  The shipped kernel (k_hamming_dense<8, 2>, carry-save compression of the
+    # eight XOR words) EXECUTES 5 POPC (XU pipe) + 14 LOP3 + 8 XOR = 22 ALU-pipe instructions per pair; utilisation is
+    # executed lane-ops / the issue rate of that pipe measured in this run.  The naive formulation needs 8 POPC per pair.
+    popc_pp, alu_pp = 5, 22
+    frac_popc = gpairs * 1e9 * popc_pp / (world * popc.value)
+    frac_alu = gpairs * 1e9 * alu_pp / (world * lop3.value)
+    return {"metric": "Hamming match Gpairs/s (2000 queries x 1M-row bank, top-2 + ratio 0.7 / TH_LOW 50)",
+            "value": gpairs, "unit": "Gpairs/s", "ms_per_step": hms, "scaling": "strong", "shards": world,
+            "verified": verified, "accepted_matches": accepted,
+            "verified_how": "records + matches of the timed (sharded) path == one scan of the gathered whole bank on every rank, bit for bit; "
+                            "4 queries of that scan == numpy popcount",
+            "exchange": ("none (one shard)" if world == 1 else "peer-memory stores over NVLink + arrival flags, fused with the shard merge; no collective call"
+                         if use_peer else "one NCCL all-gather of 16 B per query per rank + merge kernel"),
+            "roofline": {"bound": "integer-pipe", "achieved": gpairs, "unit": "Gpairs/s",
+                         "executed": {"popc_per_pair": popc_pp, "alu_per_pair": alu_pp},
+                         "frac_popc": frac_popc, "frac_alu": frac_alu, "frac": max(frac_popc, frac_alu),
+                         "peak": gpairs / max(frac_popc, frac_alu),
+                         "naive_8popc_bound_gpairs": world * popc.value / 8 / 1e9,
+                         "note": "frac = utilisation of the busier pipe by the instructions the kernel executes (5 POPC on the XU pipe, 14 LOP3 + 8 XOR "
+                                 "on the ALU pipe per pair) against the issue rates measured in this run; peak = the Gpairs/s at which that pipe "
+                                 "would be saturated; the naive bound (8 POPC per pair) is listed for reference only",
+                         "popc_per_s_measured": popc.value, "lop3_per_s_measured": lop3.value}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--pairs", type=int, default=320, help="stereo pairs per step per GPU (640 images = 299 MB > L2)")
+    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json workload: c2 = configs[1] batched (default, what the metric is "
+                    "quoted on), c1 = TUM1 single frame, c3 = EuRoC 64 pairs/GPU, c5a = 4096-frame KITTI batch, c5b = 3840x2160 @ 8000")
+    ap.add_argument("--pairs", type=int, default=0, help="stereo pairs (or mono frames) per step per GPU; 0 = the workload's own (c2: 320 pairs = 299 MB > L2)")
     ap.add_argument("--ref-pairs", type=int, default=0)
     ap.add_argument("--no-hamming", action="store_true")
     ap.add_argument("--hamming-exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the per-shard top-2 records travel: the library's peer-memory kernels (default) or one NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the informational single-pair latency loop (profiling runs)")
+    ap.add_argument("--no-copy-probe", action="store_true", help="skip the host-copy ceiling probe of the e2e leg")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
     if world == 1 and args.gpus > 1:

@@ -197,7 +197,11 @@ k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, co
   for (int k = 0; k < kPatchIters; k++)
     if (sub < 3 && 3 * k + sub < kPatchRows) patch[(3 * k + sub) * kPatchWords + word] = pw[k];
   __syncwarp();
-  const uint8_t *bc = reinterpret_cast<const uint8_t *>(patch) + kPatchR * (kPatchWords * 4) + lead + kPatchR;
+  // cvRound(x) = round-half-even = the low mantissa bits of x + 1.5 * 2^23 for |x| < 2^22 (an FADD on the FMA pipe instead of
+  // an F2I on the quarter-rate XU pipe); the two biases are folded into the base offset (bits of 1.5 * 2^23 = 0x4B400000)
+  const float kMagic = 12582912.0f;
+  const uint8_t *pb = reinterpret_cast<const uint8_t *>(patch);
+  const unsigned off0 = (unsigned)(kPatchR * (kPatchWords * 4) + lead + kPatchR) - 0x4B400000u * (unsigned)(kPatchWords * 4 + 1);   // mod 2^32
   const float2 *p = d_patternT + lane;         // point 16*lane + j sits at p[32 * j]
   unsigned val = 0;
 #pragma unroll
@@ -206,9 +210,9 @@ k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, co
 #pragma unroll
     for (int e = 0; e < 2; e++) {
       const float2 q = __ldg(&p[32 * (2 * bit + e)]);
-      const int ry = __float2int_rn(__fadd_rn(__fmul_rn(q.x, b), __fmul_rn(q.y, a)));
-      const int rx = __float2int_rn(__fsub_rn(__fmul_rn(q.x, a), __fmul_rn(q.y, b)));
-      t[e] = bc[ry * (kPatchWords * 4) + rx];
+      const unsigned ry = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(q.x, b), __fmul_rn(q.y, a)), kMagic));
+      const unsigned rx = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(q.x, a), __fmul_rn(q.y, b)), kMagic));
+      t[e] = pb[ry * (unsigned)(kPatchWords * 4) + rx + off0];
     }
     val |= (unsigned)(t[0] < t[1]) << bit;
   }

@@ -3,7 +3,7 @@
 out=${1:-gpurun_out/variants.txt}
 mkdir -p "$(dirname "$out")"
 run() {
-  python bench.py --steps 10 --warmup 3 --no-hamming --no-cpu-baseline --no-latency 2>/dev/null | python -c "
+  python bench.py --steps 10 --warmup 3 --no-hamming --no-cpu-baseline --no-latency --no-copy-probe 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 print('$1', round(d['value']), 'fps', round(d['ms_per_step'],3), 'ms', {k:round(v,3) for k,v in d['stage_ms'].items()})"

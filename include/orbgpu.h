@@ -254,6 +254,24 @@ int orbgpu_features_create(const orbgpu_features_desc *desc, orbgpu_features **o
  * (mDistCoef[0] == 0: Frame::UndistortKeyPoints copies mvKeys, src/Frame.cc:419-423). */
 int orbgpu_features_from_extractor(orbgpu_extractor *e, int image, int pair, const orbgpu_features_desc *geometry,
                                    orbgpu_features **out);
+/* Pinhole + radial-tangential camera as the reference's settings files give it (Camera.fx .. Camera.k3, e.g.
+ * Examples/Monocular/TUM1.yaml:8-17): mK and mDistCoef of src/Frame.cc, float like there. */
+typedef struct orbgpu_camera {
+  float fx, fy, cx, cy;
+  float dist[5];                      /* k1 k2 p1 p2 k3 (k3 = 0 when the file has none) */
+  int32_t ndist;                      /* 4 or 5 */
+} orbgpu_camera;
+/* orbgpu_features_from_extractor for DISTORTED input: Frame::UndistortKeyPoints (src/Frame.cc:419-445) runs on the device
+ * copy of the keypoints — cv::undistortPoints(mvKeys, mK, mDistCoef, R = I, P = mK), OpenCV 4.x's five double-precision
+ * fixed-point iterations, bit-exact against cv2 — before the grid is built, so distorted monocular / RGB-D frames need no
+ * D2H -> host -> H2D round trip between extraction and the first search.  dist[0] == 0 copies (Frame.cc:420-423). */
+int orbgpu_features_from_extractor_undistorted(orbgpu_extractor *e, int image, int pair, const orbgpu_features_desc *geometry,
+                                               const orbgpu_camera *camera, orbgpu_features **out);
+/* The same operation on host arrays: `keys_un` receives the records of `keys` with pt replaced (may alias `keys`);
+ * orbgpu_undistort_points takes bare (x, y) pairs — the four image corners of Frame::ComputeImageBounds
+ * (src/Frame.cc:447-475) go through it. */
+int orbgpu_undistort_keypoints(const orbgpu_keypoint *keys, int n, const orbgpu_camera *camera, orbgpu_keypoint *keys_un, int device);
+int orbgpu_undistort_points(const float *xy, int n, const orbgpu_camera *camera, float *xy_undistorted, int device);
 void orbgpu_features_destroy(orbgpu_features *f);
 int orbgpu_features_count(const orbgpu_features *f);
 /* Grid as CSR: cell (ix, iy) is row ix * grid_rows + iy (mGrid[ix][iy]); cell_start has cols*rows+1 entries,

@@ -188,6 +188,18 @@ def stereo(ext_l, ext_r, kl, dl, kr, dr, mbf, mb):
     return u, z, bd, kept
 
 
+def undistort_points(xy, fx, fy, cx, cy, dist):
+    """cv::undistortPoints(xy, K, dist, R=None, P=K) restated (Frame.cc:419-445); xy float32 [n, 2]."""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    d = np.ascontiguousarray(dist, np.float32).ravel()
+    out = np.empty_like(xy)
+    L = lib()
+    L.orb_oracle_undistort_points.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p]
+    L.orb_oracle_undistort_points.restype = None
+    L.orb_oracle_undistort_points(_p(xy), len(xy), fx, fy, cx, cy, _p(d), len(d), _p(out))
+    return out
+
+
 def hamming(a, b):
     return lib().orb_oracle_hamming(_p(np.ascontiguousarray(a)), _p(np.ascontiguousarray(b)))
 

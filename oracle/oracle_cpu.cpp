@@ -916,4 +916,36 @@ int orb_oracle_stereo_views(int nlevels, const uint8_t *const *planesL, const ui
   return stereo_matches_views(VL, VR, (const KeyPointRec *)kL, dL, nL, (const KeyPointRec *)kR, dR, nR, mbf, mb, uRight, depth, nullptr);
 }
 
+// cv::undistortPoints(src, dst, K, distCoeffs, R = empty, P = K) as Frame::UndistortKeyPoints (Frame.cc:419-445) and
+// Frame::ComputeImageBounds (Frame.cc:447-475) call it.  OpenCV 4.x (calib3d undistort.dispatch.cpp, cvUndistortPointsInternal)
+// with the default TermCriteria(MAX_ITER, 5, 0.01): K and the distortion coefficients (k1 k2 p1 p2 [k3], float in the
+// reference) widened to double, five fixed-point iterations in double, re-projection with P, ONE rounding to float at the
+// end.  The operation order below is the source's; pinned bit for bit against cv2 4.13 in tests/test_undistort.py.
+void orb_oracle_undistort_points(const float *xy, int n, float fxf, float fyf, float cxf, float cyf, const float *dist, int ndist,
+                                 float *out) {
+  double k[14] = {0};
+  for (int i = 0; i < ndist && i < 14; i++) k[i] = (double)dist[i];
+  const double fx = fxf, fy = fyf, cx = cxf, cy = cyf, ifx = 1. / fx, ify = 1. / fy;
+  for (int i = 0; i < n; i++) {
+    double x = xy[2 * i], y = xy[2 * i + 1];
+    const double u = x, v = y;
+    x = (x - cx) * ifx;
+    y = (y - cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; j++) {
+      const double r2 = x * x + y * y;
+      const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+      if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+      const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+      const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+      x = (x0 - deltaX) * icdist;
+      y = (y0 - deltaY) * icdist;
+    }
+    // P = K, R = identity: RR = [fx 0 cx; 0 fy cy; 0 0 1]
+    const double xx = fx * x + 0.0 * y + cx, yy = 0.0 * x + fy * y + cy, ww = 1. / (0.0 * x + 0.0 * y + 1.0);
+    out[2 * i] = (float)(xx * ww);
+    out[2 * i + 1] = (float)(yy * ww);
+  }
+}
+
 }  // extern "C"

@@ -33,6 +33,22 @@ class FeaturesDesc(C.Structure):
                 ("device", C.c_int32)]
 
 
+class Camera(C.Structure):
+    """orbgpu_camera: mK and mDistCoef of src/Frame.cc as the settings files give them (float)."""
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("dist", C.c_float * 5), ("ndist", C.c_int32)]
+
+    @classmethod
+    def make(cls, fx, fy, cx, cy, dist):
+        d = [float(np.float32(x)) for x in dist]
+        if len(d) not in (4, 5):
+            raise ValueError("4 or 5 distortion coefficients (k1 k2 p1 p2 [k3])")
+        c = cls(float(np.float32(fx)), float(np.float32(fy)), float(np.float32(cx)), float(np.float32(cy)))
+        for i, x in enumerate(d):
+            c.dist[i] = x
+        c.ndist = len(d)
+        return c
+
+
 class SearchPolicy(C.Structure):
     _fields_ = [("source", C.c_int32), ("ratio_mode", C.c_int32), ("greedy", C.c_int32), ("gate", C.c_int32),
                 ("accept_max", C.c_int32), ("ratio", C.c_float), ("stereo_gate", C.c_int32), ("only_stereo", C.c_int32),
@@ -95,6 +111,9 @@ SYMBOLS = {
     "orbgpu_hamming_top2_csr": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i]),
     "orbgpu_features_create": (_i, [C.POINTER(FeaturesDesc), C.POINTER(_vp)]),
     "orbgpu_features_from_extractor": (_i, [_vp, _i, _i, C.POINTER(FeaturesDesc), C.POINTER(_vp)]),
+    "orbgpu_features_from_extractor_undistorted": (_i, [_vp, _i, _i, C.POINTER(FeaturesDesc), C.POINTER(Camera), C.POINTER(_vp)]),
+    "orbgpu_undistort_keypoints": (_i, [_vp, _i, C.POINTER(Camera), _vp, _i]),
+    "orbgpu_undistort_points": (_i, [_vp, _i, C.POINTER(Camera), _vp, _i]),
     "orbgpu_features_destroy": (None, [_vp]),
     "orbgpu_features_count": (_i, [_vp]),
     "orbgpu_features_grid": (_i, [_vp, _vp, _vp, C.POINTER(C.c_int32)]),

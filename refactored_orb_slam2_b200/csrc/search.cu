@@ -110,6 +110,42 @@ __global__ void k_grid_sort(const int *cellStart, int *items, int ncells) {
   }
 }
 
+// cv::undistortPoints(src, dst, K, distCoeffs, R = empty, P = K) as Frame::UndistortKeyPoints (src/Frame.cc:419-445) and
+// Frame::ComputeImageBounds (:447-475) call it: OpenCV 4.x cvUndistortPointsInternal with its default TermCriteria
+// (MAX_ITER 5): float K and (k1 k2 p1 p2 [k3]) widened to double, five fixed-point iterations in double in the source's
+// operation order (round-to-nearest intrinsics: nothing is fused), ONE rounding to float.  One thread per point; `stride`
+// floats between consecutive points (2 for bare points, 7 for the pt field of 28-byte cv::KeyPoint records).
+struct CameraDev { double fx, fy, cx, cy, ifx, ify, k[5]; };
+__global__ void k_undistort(const float *src, float *dst, int n, int stride, const CameraDev C) {   // src may alias dst
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double u = (double)src[(size_t)i * stride], v = (double)src[(size_t)i * stride + 1];
+  double x = __dmul_rn(__dsub_rn(u, C.cx), C.ifx), y = __dmul_rn(__dsub_rn(v, C.cy), C.ify);
+  const double x0 = x, y0 = y;
+#pragma unroll 1
+  for (int j = 0; j < 5; j++) {
+    const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+    // (1 + ((k7 r2 + k6) r2 + k5) r2) with k5 = k6 = k7 = 0 is exactly 1
+    const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(C.k[4], r2), C.k[1]), r2), C.k[0]), r2));
+    const double icdist = __ddiv_rn(1.0, den);
+    if (icdist < 0) { x = x0; y = y0; break; }            // (u - cx) ifx again: the value x started from
+    // deltaX = 2 k2 x y + k3 (r2 + 2 x x) [+ k8 r2 + k9 r2 r2 = +0], deltaY = k2 (r2 + 2 y y) + 2 k3 x y [+ 0]
+    const double dX = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, C.k[2]), x), y), __dmul_rn(C.k[3], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x))));
+    const double dY = __dadd_rn(__dmul_rn(C.k[2], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y))), __dmul_rn(__dmul_rn(__dmul_rn(2.0, C.k[3]), x), y));
+    x = __dmul_rn(__dsub_rn(x0, dX), icdist);
+    y = __dmul_rn(__dsub_rn(y0, dY), icdist);
+  }
+  // P = K, R = identity: xx = fx x + 0 y + cx, ww = 1 / (0 x + 0 y + 1) = 1
+  dst[(size_t)i * stride] = (float)__dadd_rn(__dmul_rn(C.fx, x), C.cx);
+  dst[(size_t)i * stride + 1] = (float)__dadd_rn(__dmul_rn(C.fy, y), C.cy);
+}
+CameraDev to_device_camera(const orbgpu_camera &c) {
+  CameraDev C;
+  C.fx = c.fx; C.fy = c.fy; C.cx = c.cx; C.cy = c.cy; C.ifx = 1. / C.fx; C.ify = 1. / C.fy;
+  for (int i = 0; i < 5; i++) C.k[i] = i < c.ndist ? (double)c.dist[i] : 0.0;
+  return C;
+}
+
 __global__ void k_fill_float(float *p, int n, float v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -479,7 +515,8 @@ int orbgpu_features_create(const orbgpu_features_desc *desc, orbgpu_features **o
   return ORBGPU_OK;
 }
 
-int orbgpu_features_from_extractor(orbgpu_extractor *e, int image, int pair, const orbgpu_features_desc *geometry, orbgpu_features **out) {
+static int features_from_extractor(orbgpu_extractor *e, int image, int pair, const orbgpu_features_desc *geometry, const orbgpu_camera *cam,
+                                   orbgpu_features **out) {
   if (!out) { set_error("null output"); return ORBGPU_E_INVALID; }
   *out = nullptr;
   if (!e || !geometry) { set_error("null argument"); return ORBGPU_E_INVALID; }
@@ -502,12 +539,63 @@ int orbgpu_features_from_extractor(orbgpu_extractor *e, int image, int pair, con
       if (uRight) ce = cudaMemcpyAsync(f->dURight, uRight, (size_t)count * sizeof(float), cudaMemcpyDeviceToDevice, s);
       else { k_fill_float<<<(count + 255) / 256, 256, 0, s>>>(f->dURight, count, -1.f); count_launch(); ce = cudaGetLastError(); }
     }
+    // distorted input: mvKeysUn = cv::undistortPoints(mvKeys) in place, before the grid is built from it (Frame.cc:122, 419-445)
+    if (ce == cudaSuccess && cam && cam->dist[0] != 0.0f) {
+      k_undistort<<<(count + 127) / 128, 128, 0, s>>>(reinterpret_cast<const float *>(f->dKps), reinterpret_cast<float *>(f->dKps), count,
+                                                      (int)(sizeof(orbgpu_keypoint) / sizeof(float)), to_device_camera(*cam));
+      count_launch();
+      ce = cudaGetLastError();
+    }
     if (ce != cudaSuccess) { set_error("feature copy failed: %s", cudaGetErrorString(ce)); rc = ORBGPU_E_CUDA; }
   }
   if (rc == ORBGPU_OK) rc = build_grid(f, (cudaStream_t)stream);
   if (rc != ORBGPU_OK) { orbgpu_features_destroy(f); return rc; }
   *out = f;
   return ORBGPU_OK;
+}
+
+int orbgpu_features_from_extractor(orbgpu_extractor *e, int image, int pair, const orbgpu_features_desc *geometry, orbgpu_features **out) {
+  return features_from_extractor(e, image, pair, geometry, nullptr, out);
+}
+int orbgpu_features_from_extractor_undistorted(orbgpu_extractor *e, int image, int pair, const orbgpu_features_desc *geometry,
+                                               const orbgpu_camera *camera, orbgpu_features **out) {
+  if (!camera) { set_error("null camera"); return ORBGPU_E_INVALID; }
+  if (camera->ndist < 4 || camera->ndist > 5 || !(camera->fx != 0.f) || !(camera->fy != 0.f)) { set_error("camera: need fx, fy != 0 and 4 or 5 distortion coefficients"); return ORBGPU_E_INVALID; }
+  return features_from_extractor(e, image, pair, geometry, camera, out);
+}
+
+static int undistort_host(const float *src, float *dst, int n, int stride, const orbgpu_camera *camera, int device) {
+  if (n < 0 || !camera || (n > 0 && (!src || !dst))) { set_error("bad arguments"); return ORBGPU_E_INVALID; }
+  if (camera->ndist < 4 || camera->ndist > 5 || !(camera->fx != 0.f) || !(camera->fy != 0.f)) { set_error("camera: need fx, fy != 0 and 4 or 5 distortion coefficients"); return ORBGPU_E_INVALID; }
+  if (n == 0) return ORBGPU_OK;
+  if (camera->dist[0] == 0.0f) {               // Frame.cc:420-423: mvKeysUn = mvKeys
+    if (dst != src) std::memcpy(dst, src, (size_t)n * stride * sizeof(float));
+    return ORBGPU_OK;
+  }
+  if (orbgpu_device_count() < 1) { set_error("no CUDA device available (this library has no CPU path)"); return ORBGPU_E_CUDA; }
+  DevGuard guard(device);
+  if (!guard.ok) { set_error("cannot select device %d", device); return ORBGPU_E_CUDA; }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const size_t bytes = (size_t)n * stride * sizeof(float);
+  Workspace &W = t_ws;
+  cudaError_t e = ensure(W, dev, bytes, 0, 0);
+  if (e != cudaSuccess) { set_error("workspace allocation failed: %s", cudaGetErrorString(e)); return ORBGPU_E_CUDA; }
+  std::memcpy(W.hStage, src, bytes);
+  ORBGPU_CUDA_CHECK(cudaMemcpyAsync(W.dStage, W.hStage, bytes, cudaMemcpyHostToDevice, W.stream));
+  k_undistort<<<(n + 127) / 128, 128, 0, W.stream>>>(reinterpret_cast<const float *>(W.dStage), reinterpret_cast<float *>(W.dStage), n, stride, to_device_camera(*camera));
+  count_launch();
+  ORBGPU_CUDA_CHECK(cudaGetLastError());
+  ORBGPU_CUDA_CHECK(cudaMemcpyAsync(W.hStage, W.dStage, bytes, cudaMemcpyDeviceToHost, W.stream));
+  ORBGPU_CUDA_CHECK(cudaStreamSynchronize(W.stream));
+  std::memcpy(dst, W.hStage, bytes);
+  return ORBGPU_OK;
+}
+int orbgpu_undistort_points(const float *xy, int n, const orbgpu_camera *camera, float *xy_undistorted, int device) {
+  return undistort_host(xy, xy_undistorted, n, 2, camera, device);
+}
+int orbgpu_undistort_keypoints(const orbgpu_keypoint *keys, int n, const orbgpu_camera *camera, orbgpu_keypoint *keys_un, int device) {
+  return undistort_host(reinterpret_cast<const float *>(keys), reinterpret_cast<float *>(keys_un), n, (int)(sizeof(orbgpu_keypoint) / sizeof(float)), camera, device);
 }
 
 void orbgpu_features_destroy(orbgpu_features *f) {

@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import KP_DTYPE, MATCH_DTYPE, QUERY_DTYPE, FeaturesDesc, SearchPolicy, check, lib, ptr
+from ._lib import KP_DTYPE, MATCH_DTYPE, QUERY_DTYPE, Camera, FeaturesDesc, SearchPolicy, check, lib, ptr
 
 FRAME_GRID_COLS, FRAME_GRID_ROWS = 64, 48          # include/Frame.h:35-36
 SRC_WINDOW, SRC_LIST = 0, 1
@@ -46,6 +46,31 @@ def make_policy(source=SRC_WINDOW, ratio_mode=RATIO_NONE, greedy=GREEDY_NONE, ac
     return P
 
 
+def UndistortKeyPoints(keys, camera, device=-1):
+    """Frame::UndistortKeyPoints (Frame.cc:419-445): mvKeysUn = mvKeys with pt = cv::undistortPoints(pt, mK, mDistCoef, P = mK),
+    a copy when mDistCoef[0] == 0.  `camera` is a _lib.Camera (Camera.make(fx, fy, cx, cy, [k1, k2, p1, p2, k3]))."""
+    k = np.ascontiguousarray(keys, KP_DTYPE)
+    out = np.empty_like(k)
+    check(lib().orbgpu_undistort_keypoints(ptr(k), len(k), C.byref(camera), ptr(out), device))
+    return out
+
+
+def undistort_points(xy, camera, device=-1):
+    """cv::undistortPoints on bare float32 (x, y) pairs — the image corners of Frame::ComputeImageBounds (Frame.cc:447-475)."""
+    p = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    out = np.empty_like(p)
+    check(lib().orbgpu_undistort_points(ptr(p), len(p), C.byref(camera), ptr(out), device))
+    return out
+
+
+def ComputeImageBounds(width, height, camera, device=-1):
+    """Frame::ComputeImageBounds (Frame.cc:447-475): (mnMinX, mnMaxX, mnMinY, mnMaxY)."""
+    if camera is None or camera.dist[0] == 0.0:
+        return np.float32(0), np.float32(width), np.float32(0), np.float32(height)
+    m = undistort_points([[0, 0], [width, 0], [0, height], [width, height]], camera, device)
+    return min(m[0, 0], m[2, 0]), max(m[1, 0], m[3, 0]), min(m[0, 1], m[1, 1]), max(m[2, 1], m[3, 1])
+
+
 class FrameFeatures:
     def __init__(self, keys_un=None, descriptors=None, u_right=None, geometry=None, *, _handle=None):
         if _handle is not None:
@@ -65,10 +90,15 @@ class FrameFeatures:
         self.n = lib().orbgpu_features_count(self._h)
 
     @classmethod
-    def from_extractor(cls, extractor, image, geometry, pair=-1):
-        """Device-to-device from the last extract_batch of `extractor` (and row `pair` of its last stereo match)."""
+    def from_extractor(cls, extractor, image, geometry, pair=-1, camera=None):
+        """Device-to-device from the last extract_batch of `extractor` (and row `pair` of its last stereo match).  With a
+        `camera` whose k1 != 0 the keypoints are undistorted on the device first (Frame::UndistortKeyPoints)."""
         out = C.c_void_p()
-        check(lib().orbgpu_features_from_extractor(extractor._h, int(image), int(pair), C.byref(geometry), C.byref(out)))
+        if camera is None:
+            check(lib().orbgpu_features_from_extractor(extractor._h, int(image), int(pair), C.byref(geometry), C.byref(out)))
+        else:
+            check(lib().orbgpu_features_from_extractor_undistorted(extractor._h, int(image), int(pair), C.byref(geometry), C.byref(camera),
+                                                                   C.byref(out)))
         return cls(_handle=out)
 
     def close(self):

@@ -414,6 +414,33 @@ int orbgpu_remap(const uint8_t *src, int src_width, int src_height, const float 
 int orbgpu_distinctive_descriptors(const uint8_t *descriptors, const int32_t *offsets, int groups, int32_t *best_index,
                                    int32_t *best_median, int device);
 
+/* ------------------------------------------------------------------------------------------------
+ * KeyFrameDatabase candidate scoring (second half)
+ *
+ * src/KeyFrameDatabase.cc:72-306 (DetectLoopCandidates, DetectRelocalizationCandidates): walk the inverted file over
+ * the query's words to count, per keyframe, the words it shares with the query (mnLoopWords / mnRelocWords), keep
+ * the keyframes above 0.8 x the best count, and score each against the query with DBoW2's L1 score
+ * (ThirdParty/DBoW2/DBoW2-local/src/ScoringObject.cpp:23-67).  Here the database keeps every keyframe's BowVector
+ * resident in HBM and ONE query call returns, for every slot at once: the shared-word count, the smallest shared word
+ * id (0xffffffff if none) — with the slot number it orders the keyframes exactly as the inverted-file walk meets them
+ * first — and the L1 score as the double DBoW2 computes (terms added in ascending word order), which the caller narrows
+ * to float like `float si = mpVoc->score(...)`.  The covisibility accumulation that follows (:140-166, :248-275) walks
+ * the KeyFrame pointer graph and stays on the host (shim/KeyFrameDatabase.cc).
+ * Slots are handed out in add() order and never reused (that order IS the push_back order of each inverted-file list);
+ * erase marks a slot dead; clear drops everything.  Word ids must be strictly ascending (a BowVector is a std::map).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct orbgpu_bowdb orbgpu_bowdb;
+int orbgpu_bowdb_create(int device, orbgpu_bowdb **out);
+void orbgpu_bowdb_destroy(orbgpu_bowdb *db);
+/* KeyFrameDatabase::add (:38-46): returns the new slot (>= 0) or a negative error code. */
+int orbgpu_bowdb_add(orbgpu_bowdb *db, const uint32_t *word_ids, const double *weights, int n);
+int orbgpu_bowdb_erase(orbgpu_bowdb *db, int slot);           /* KeyFrameDatabase::erase (:48-66) */
+int orbgpu_bowdb_clear(orbgpu_bowdb *db);                     /* KeyFrameDatabase::clear (:68-71) */
+int orbgpu_bowdb_slots(const orbgpu_bowdb *db);               /* slots handed out so far (dead ones included) */
+/* Result arrays hold `capacity` >= orbgpu_bowdb_slots(db) entries; dead slots report 0 / 0xffffffff / 0. */
+int orbgpu_bowdb_query(orbgpu_bowdb *db, const uint32_t *word_ids, const double *weights, int n, int32_t *common_words,
+                       uint32_t *first_common_word, double *score, int capacity);
+
 /* Measured integer-pipe peak (register-resident POPC loop): returns POPC lane-ops per second. */
 int orbgpu_measure_popc_peak(int device, double *popc_per_second, double *lop3_per_second);
 /* Issue rate of one instruction kind in lane-operations per second (register-resident loop): mode 0 POPC, 1 LOP3,

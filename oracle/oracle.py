@@ -200,6 +200,25 @@ def undistort_points(xy, fx, fy, cx, cy, dist):
     return out
 
 
+def bow_query(database, query, alive=None):
+    """KeyFrameDatabase candidate scoring for every keyframe of `database` (list of (ascending word ids, weights)) against
+    `query`: (shared words, first shared word, DBoW2 L1 score as float64)."""
+    n = len(database)
+    start = np.zeros(n + 1, np.int32)
+    start[1:] = np.cumsum([len(i) for i, _ in database])
+    words = np.concatenate([np.asarray(i, np.uint32) for i, _ in database]) if n else np.zeros(0, np.uint32)
+    weights = np.concatenate([np.asarray(w, np.float64) for _, w in database]) if n else np.zeros(0)
+    live = np.ones(n, np.uint8) if alive is None else np.ascontiguousarray(alive, np.uint8)
+    qi, qw = np.ascontiguousarray(query[0], np.uint32), np.ascontiguousarray(query[1], np.float64)
+    common, first, score = np.zeros(n, np.int32), np.zeros(n, np.uint32), np.zeros(n, np.float64)
+    L = lib()
+    L.orb_oracle_bow_query.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 3
+    L.orb_oracle_bow_query.restype = None
+    L.orb_oracle_bow_query(n, _p(start), _p(np.ascontiguousarray(words)), _p(np.ascontiguousarray(weights)), _p(live), _p(qi), _p(qw), len(qi),
+                           _p(common), _p(first), _p(score))
+    return common, first, score
+
+
 def hamming(a, b):
     return lib().orb_oracle_hamming(_p(np.ascontiguousarray(a)), _p(np.ascontiguousarray(b)))
 

@@ -948,4 +948,34 @@ void orb_oracle_undistort_points(const float *xy, int n, float fxf, float fyf, f
   }
 }
 
+// KeyFrameDatabase candidate scoring (KeyFrameDatabase.cc:81-132, 195-241) for every keyframe of a CSR database at once:
+// words shared with the query, the smallest shared word, and DBoW2's L1 score (ScoringObject.cpp:23-67: merge of the two
+// ascending BowVectors, score += fabs(vi - wi) - fabs(vi) - fabs(wi) on equal ids with v = query, w = keyframe, then
+// -score / 2).  Pinned to the reference's own KeyFrameDatabase.cc + DBoW2 in tests/test_kfdb_ref.py.
+void orb_oracle_bow_query(int slots, const int *start, const uint32_t *words, const double *weights, const uint8_t *alive,
+                          const uint32_t *qWords, const double *qWeights, int nq, int32_t *common, uint32_t *firstWord, double *score) {
+  for (int s = 0; s < slots; s++) {
+    int n = 0;
+    uint32_t first = 0xffffffffu;
+    double sc = 0;
+    if (alive[s]) {
+      int a = 0, b = start[s];
+      const int bend = start[s + 1];
+      while (a < nq && b < bend) {
+        if (qWords[a] == words[b]) {
+          const double vi = qWeights[a], wi = weights[b];
+          sc += std::fabs(vi - wi) - std::fabs(vi) - std::fabs(wi);
+          if (!n) first = words[b];
+          n++; a++; b++;
+        } else if (qWords[a] < words[b]) {
+          a++;
+        } else {
+          b++;
+        }
+      }
+    }
+    common[s] = n; firstWord[s] = first; score[s] = -sc / 2.0;
+  }
+}
+
 }  // extern "C"

@@ -83,5 +83,30 @@ int orbgpu_search(orbgpu_features *f, const orbgpu_query *queries, const uint8_t
   }
   return rc;
 }
+// ---- KeyFrameDatabase scoring (shim/KeyFrameDatabase.cc on the CPU): the database as the same CSR the device keeps
+void orb_oracle_bow_query(int slots, const int *start, const uint32_t *words, const double *weights, const uint8_t *alive,
+                          const uint32_t *qWords, const double *qWeights, int nq, int32_t *common, uint32_t *firstWord, double *score);
+struct OracleBowDb { std::vector<int> start{0}; std::vector<uint32_t> words; std::vector<double> weights; std::vector<uint8_t> alive; };
+int orbgpu_bowdb_create(int, orbgpu_bowdb **out) { *out = reinterpret_cast<orbgpu_bowdb *>(new OracleBowDb); return ORBGPU_OK; }
+void orbgpu_bowdb_destroy(orbgpu_bowdb *db) { delete reinterpret_cast<OracleBowDb *>(db); }
+int orbgpu_bowdb_slots(const orbgpu_bowdb *db) { return (int)reinterpret_cast<const OracleBowDb *>(db)->alive.size(); }
+int orbgpu_bowdb_add(orbgpu_bowdb *h, const uint32_t *word_ids, const double *weights, int n) {
+  OracleBowDb *db = reinterpret_cast<OracleBowDb *>(h);
+  db->words.insert(db->words.end(), word_ids, word_ids + n);
+  db->weights.insert(db->weights.end(), weights, weights + n);
+  db->start.push_back((int)db->words.size());
+  db->alive.push_back(1);
+  return (int)db->alive.size() - 1;
+}
+int orbgpu_bowdb_erase(orbgpu_bowdb *h, int slot) { reinterpret_cast<OracleBowDb *>(h)->alive[slot] = 0; return ORBGPU_OK; }
+int orbgpu_bowdb_clear(orbgpu_bowdb *h) { *reinterpret_cast<OracleBowDb *>(h) = OracleBowDb(); return ORBGPU_OK; }
+int orbgpu_bowdb_query(orbgpu_bowdb *h, const uint32_t *word_ids, const double *weights, int n, int32_t *common_words, uint32_t *first_common_word,
+                       double *score, int capacity) {
+  OracleBowDb *db = reinterpret_cast<OracleBowDb *>(h);
+  if (capacity < (int)db->alive.size()) return ORBGPU_E_CAPACITY;
+  orb_oracle_bow_query((int)db->alive.size(), db->start.data(), db->words.data(), db->weights.data(), db->alive.data(), word_ids, weights, n,
+                       common_words, first_common_word, score);
+  return ORBGPU_OK;
+}
 const char *orbgpu_last_error(void) { return "oracle backend"; }
 }

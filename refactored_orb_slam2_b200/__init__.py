@@ -8,7 +8,8 @@ from .matcher import DescriptorBank, ORBmatcher, distinctive_descriptors, merge_
 from .stereo import ComputeStereoMatches, Frame  # noqa: F401
 from .pipeline import StereoBatchPipeline  # noqa: F401
 from .vocabulary import Vocabulary  # noqa: F401
+from .bowdb import BowDatabase  # noqa: F401
 from . import staging  # noqa: F401
 
-__all__ = ["ORBextractor", "FrameFeatures", "Camera", "UndistortKeyPoints", "undistort_points", "ComputeImageBounds", "grid_geometry", "make_policy", "Vocabulary", "distinctive_descriptors", "ORBmatcher", "DescriptorBank", "ComputeStereoMatches", "Frame", "StereoBatchPipeline", "merge_top2_device",
+__all__ = ["ORBextractor", "FrameFeatures", "Camera", "UndistortKeyPoints", "undistort_points", "ComputeImageBounds", "grid_geometry", "make_policy", "Vocabulary", "BowDatabase", "distinctive_descriptors", "ORBmatcher", "DescriptorBank", "ComputeStereoMatches", "Frame", "StereoBatchPipeline", "merge_top2_device",
            "KP_DTYPE", "TOP2_DTYPE", "OrbGpuError", "lib"]

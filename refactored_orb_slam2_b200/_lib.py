@@ -129,6 +129,13 @@ SYMBOLS = {
     "orbgpu_cvt_gray": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i]),
     "orbgpu_remap": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i]),
     "orbgpu_distinctive_descriptors": (_i, [_vp, _vp, _i, _vp, _vp, _i]),
+    "orbgpu_bowdb_create": (_i, [_i, C.POINTER(_vp)]),
+    "orbgpu_bowdb_destroy": (None, [_vp]),
+    "orbgpu_bowdb_add": (_i, [_vp, _vp, _vp, _i]),
+    "orbgpu_bowdb_erase": (_i, [_vp, _i]),
+    "orbgpu_bowdb_clear": (_i, [_vp]),
+    "orbgpu_bowdb_slots": (_i, [_vp]),
+    "orbgpu_bowdb_query": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i]),
     "orbgpu_measure_popc_peak": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "orbgpu_measure_pipe": (_i, [_i, _i, C.POINTER(C.c_double)]),
     "orbgpu_launch_count": (_i64, [_i]),

@@ -441,6 +441,12 @@ int orbgpu_bowdb_slots(const orbgpu_bowdb *db);               /* slots handed ou
 int orbgpu_bowdb_query(orbgpu_bowdb *db, const uint32_t *word_ids, const double *weights, int n, int32_t *common_words,
                        uint32_t *first_common_word, double *score, int capacity);
 
+/* Parity hook for computeOrbDescriptor's cos / sin (src/ORBextractor.cc:102-106): evaluates the DEVICE sincos of the
+ * descriptor kernel (glibc's sincosf algorithm, see csrc/describe.cu) on the `count` consecutive float32 bit patterns from
+ * `first_bits`.  sums (optional, host, one uint64 per 2^chunk_log2 patterns): sum over the chunk of
+ * ((sin bits << 32) | cos bits) * (0x9E3779B97F4A7C15 + 2 * pattern) mod 2^64 — the host forms the same sum with libm, so
+ * every float of [0, 2 pi] is compared without moving it; sin_values / cos_values (optional, count <= 2^26): the raw values. */
+int orbgpu_selftest_sincos(uint32_t first_bits, uint64_t count, int chunk_log2, uint64_t *sums, float *sin_values, float *cos_values, int device);
 /* Measured integer-pipe peak (register-resident POPC loop): returns POPC lane-ops per second. */
 int orbgpu_measure_popc_peak(int device, double *popc_per_second, double *lop3_per_second);
 /* Issue rate of one instruction kind in lane-operations per second (register-resident loop): mode 0 POPC, 1 LOP3,

@@ -978,4 +978,24 @@ void orb_oracle_bow_query(int slots, const int *start, const uint32_t *words, co
   }
 }
 
+// Host side of orbgpu_selftest_sincos: the same per-chunk checksum with THIS host's libm cosf / sinf (what the reference's
+// computeOrbDescriptor calls, ORBextractor.cc:104), over `count` consecutive float32 bit patterns, on `nthreads` threads.
+void orb_oracle_sincos_checksum(uint32_t firstBits, uint64_t count, int chunkLog2, uint64_t *sums, int nthreads) {
+  const uint64_t chunk = 1ull << chunkLog2, chunks = (count + chunk - 1) >> chunkLog2;
+  parallel_for((int)chunks, nthreads, [&](int c, int) {
+    uint64_t h = 0;
+    const uint64_t lo = (uint64_t)c << chunkLog2, hi = std::min(count, lo + chunk);
+    for (uint64_t i = lo; i < hi; i++) {
+      const uint32_t bits = firstBits + (uint32_t)i;
+      float x;
+      std::memcpy(&x, &bits, 4);
+      const float sn = sinf(x), cs = cosf(x);
+      uint32_t sb, cb;
+      std::memcpy(&sb, &sn, 4); std::memcpy(&cb, &cs, 4);
+      h += (((uint64_t)sb << 32) | cb) * (0x9E3779B97F4A7C15ull + 2ull * bits);
+    }
+    sums[c] = h;
+  });
+}
+
 }  // extern "C"

@@ -136,6 +136,7 @@ SYMBOLS = {
     "orbgpu_bowdb_clear": (_i, [_vp]),
     "orbgpu_bowdb_slots": (_i, [_vp]),
     "orbgpu_bowdb_query": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i]),
+    "orbgpu_selftest_sincos": (_i, [C.c_uint32, C.c_uint64, _i, _vp, _vp, _vp, _i]),
     "orbgpu_measure_popc_peak": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "orbgpu_measure_pipe": (_i, [_i, _i, C.POINTER(C.c_double)]),
     "orbgpu_launch_count": (_i64, [_i]),

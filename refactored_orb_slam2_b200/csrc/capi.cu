@@ -1217,6 +1217,34 @@ int orbgpu_measure_popc_peak(int device, double *popc_per_second, double *lop3_p
   return ORBGPU_OK;
 }
 
+int orbgpu_selftest_sincos(uint32_t first_bits, uint64_t count, int chunk_log2, uint64_t *sums, float *sin_values, float *cos_values, int device) {
+  if (chunk_log2 < 5 || chunk_log2 > 30 || count == 0 || (uint64_t)first_bits + count > 0x100000000ull) { set_error("bad range"); return ORBGPU_E_INVALID; }
+  if (orbgpu_device_count() < 1) { set_error("no CUDA device available (this library has no CPU path)"); return ORBGPU_E_CUDA; }
+  DeviceGuard guard(device);
+  if (sums) {
+    const size_t chunks = (size_t)((count + (1ull << chunk_log2) - 1) >> chunk_log2);
+    unsigned long long *d = nullptr;
+    ORBGPU_CUDA_CHECK(cudaMalloc(&d, chunks * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemset(d, 0, chunks * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = launch_sincos_checksum(first_bits, count, chunk_log2, d, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(sums, d, chunks * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { set_error("sincos selftest: %s", cudaGetErrorString(e)); return ORBGPU_E_CUDA; }
+  }
+  if (sin_values && cos_values) {
+    if (count > (1u << 26)) { set_error("value dump limited to 2^26 patterns"); return ORBGPU_E_INVALID; }
+    float *ds = nullptr, *dc = nullptr;
+    cudaError_t e = cudaMalloc(&ds, count * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&dc, count * sizeof(float));
+    if (e == cudaSuccess) e = launch_sincos_values(first_bits, (int)count, ds, dc, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(sin_values, ds, count * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(cos_values, dc, count * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(ds); cudaFree(dc);
+    if (e != cudaSuccess) { set_error("sincos selftest: %s", cudaGetErrorString(e)); return ORBGPU_E_CUDA; }
+  }
+  return ORBGPU_OK;
+}
+
 int orbgpu_measure_pipe(int device, int mode, double *ops_per_second) {
   if (!ops_per_second) { set_error("null output"); return ORBGPU_E_INVALID; }
   if (orbgpu_device_count() < 1) { set_error("no CUDA device available (this library has no CPU path)"); return ORBGPU_E_CUDA; }

@@ -233,6 +233,47 @@ k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, co
 
 }  // namespace
 
+#ifndef ORBGPU_VARIANT_IS_SECONDARY
+// ---- parity hook for the descriptor's trigonometry: the device sincos above over a RANGE of float32 bit patterns, reduced
+// to one 64-bit checksum per 2^chunkLog2 consecutive patterns so that all ~1.09 G floats of [0, 2 pi] can be compared with the
+// host libm without moving 8 GB (tests/test_gpu_sincos.py; the host side of the sum is oracle/orb_oracle_sincos_checksum)
+namespace {
+__device__ __forceinline__ unsigned long long sincos_hash(unsigned bits, float s, float c) {
+  return (((unsigned long long)__float_as_uint(s) << 32) | __float_as_uint(c)) * (0x9E3779B97F4A7C15ull + 2ull * bits);
+}
+__global__ void __launch_bounds__(256) k_sincos_checksum(unsigned firstBits, unsigned long long count, int chunkLog2, unsigned long long *sums) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  // consecutive threads take consecutive patterns; a warp's 32 patterns fall into one chunk (chunks are multiples of 32)
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((count + 31) & ~31ull); i += stride) {
+    unsigned long long h = 0;
+    if (i < count) {
+      const unsigned bits = firstBits + (unsigned)i;
+      float sn, cs;
+      sincos_glibc(__uint_as_float(bits), &sn, &cs);
+      h = sincos_hash(bits, sn, cs);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sums[i >> chunkLog2], h);
+  }
+}
+__global__ void k_sincos_values(unsigned firstBits, int n, float *s, float *c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sincos_glibc(__uint_as_float(firstBits + (unsigned)i), &s[i], &c[i]);
+}
+}  // namespace
+cudaError_t launch_sincos_checksum(unsigned firstBits, unsigned long long count, int chunkLog2, unsigned long long *dSums, cudaStream_t st) {
+  k_sincos_checksum<<<148 * 16, 256, 0, st>>>(firstBits, count, chunkLog2, dSums);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_sincos_values(unsigned firstBits, int n, float *dS, float *dC, cudaStream_t st) {
+  k_sincos_values<<<(n + 255) / 256, 256, 0, st>>>(firstBits, n, dS, dC);
+  count_launch();
+  return cudaGetLastError();
+}
+#endif
+
 // Fills this variant's d_patternT on the current device.  Called from orbgpu_extractor_create — outside any stream capture
 // (small batches replay a captured graph, and a synchronize inside the capture would invalidate it) — and complete on
 // return, so every stream that launches k_describe afterwards sees the table.

@@ -138,6 +138,8 @@ cudaError_t launch_octree(const LevelTable &T, const ExtractBuffers &B, int imgB
                           cudaStream_t s);
 int hamming_dense_q(int nq);
 cudaError_t launch_describe(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, cudaStream_t s);
+cudaError_t launch_sincos_checksum(unsigned firstBits, unsigned long long count, int chunkLog2, unsigned long long *dSums, cudaStream_t s);
+cudaError_t launch_sincos_values(unsigned firstBits, int n, float *dS, float *dC, cudaStream_t s);
 cudaError_t describe_prepare();       // pattern table of the variant, once per device, outside stream capture
 cudaError_t describe_prepare_lat();
 // second thread shape of octree / describe / stereo for small batches (octree_lat.cu, describe_lat.cu, stereo_lat.cu)

@@ -51,14 +51,17 @@ def test_ties_lowest_index_wins(pkg):
     assert np.array_equal(idx1, oi) and np.array_equal(d2, o2)
 
 
-def test_full_config4_properties(pkg):
-    """BASELINE.json configs[3] at full size (2000 x 1M), checked through properties the oracle does
-    not need to scan for: numpy popcount on a query subset, planted sources found, policy applied."""
+def test_full_config4_exact(pkg):
+    """BASELINE.json configs[3] at full size (2000 x 1M): ALL 2000 queries against the oracle's whole-bank scan (2 x 10^9
+    pairs on every host thread), numpy popcount on a query subset as a third opinion, planted sources found, policy applied."""
+    import os
     bank = gen_synth.descriptor_bank(1_000_000, 4)
     q, bank, src = gen_synth.queries_from_bank(bank, 2000, 5)
     m = pkg.ORBmatcher(0.7)
     db = pkg.DescriptorBank(bank)
     idx1, d1, d2 = db.top2(q)
+    oi, o1, o2 = oracle.top2_dense(q, bank, os.cpu_count() or 1)
+    assert np.array_equal(idx1, oi) and np.array_equal(d1, o1) and np.array_equal(d2, o2)
     for i in (0, 1, 7, 500, 1999):
         d = np_hamming_rows(q[i], bank)
         order = np.argsort(d, kind="stable")

@@ -1,10 +1,10 @@
 // Image pyramid: ORBextractor::ComputePyramid (ORBextractor.cc:1041-1065).
 //
 // Every level lives in HBM as a [batch] array of padded planes: interior w x h surrounded by the
-// reference's 19 px BORDER_REFLECT_101 apron, row pitch a multiple of 16 bytes.  Both kernels
-// write whole padded planes in one pass: a thread produces 4 consecutive padded bytes (one 32-bit
-// store), mapping each through reflect-101 to the interior pixel it mirrors, so no second
-// copyMakeBorder pass (and no re-read of the level) is needed.
+// reference's 19 px BORDER_REFLECT_101 apron, row pitch a multiple of 16 bytes.  The import and the
+// generic resize write whole padded planes in one pass (every padded byte mapped through reflect-101
+// to the interior pixel it mirrors); the tiled resize writes the interior rows with their side aprons
+// and one small copy kernel adds the apron rows of all levels at the end.
 //
 // Level l >= 1 is cv::resize(level l-1, INTER_LINEAR) in OpenCV's 11-bit fixed point:
 //   H(x)   = S[xo]*a0 + S[xo+1]*a1                      (int32, a0+a1 = 2048)
@@ -24,30 +24,39 @@ __device__ __forceinline__ int reflect101(int p, int n) {
   return p >= n ? 2 * (n - 1) - p : p;
 }
 
+// Level 0 = the input image inside its apron.  One thread = 16 padded bytes = one 128-bit store.  Interior chunks gather their
+// 16 source bytes from five aligned 32-bit words re-aligned by funnel shifts (the source rows of a 1241-pixel image start on
+// any byte); chunks that touch the left / right apron take the byte path with the reflect-101 index.
 __global__ void __launch_bounds__(256)
 k_import_level0(const __grid_constant__ LevelGeom G, uint8_t *__restrict__ pyr, const uint8_t *__restrict__ src,
                 size_t rowStep, size_t imgStep, int imgBase) {   // level-0 geometry by value: no dependent table loads in front of the copy
   const int img = imgBase + blockIdx.z;
   const int py = blockIdx.y * blockDim.y + threadIdx.y;
-  const int px4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (py >= G.rows || px4 >= G.pitch) return;
-  const uint8_t *S = src + (size_t)img * imgStep + (size_t)reflect101(py - kEdge, G.h) * rowStep;
-  unsigned out;
-  if (px4 >= kEdge && px4 + 3 < G.w + kEdge) {      // four interior pixels: no mirroring
-    const uint8_t *p = S + (px4 - kEdge);
-    out = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24);
+  const int px16 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (py >= G.rows || px16 >= G.pitch) return;
+  const int sy = reflect101(py - kEdge, G.h);
+  const uint8_t *S = src + (size_t)img * imgStep + (size_t)sy * rowStep;
+  uint4 out;
+  // sixteen interior pixels: no mirroring (the word that holds the chunk's last byte may run 3 bytes past it: on the image's
+  // last row the final chunk takes the byte path instead of reading past the caller's buffer)
+  if (px16 >= kEdge && px16 + 15 < G.w + kEdge && (sy != G.h - 1 || px16 + 19 < G.w + kEdge)) {
+    const uint8_t *p = S + (px16 - kEdge);
+    const unsigned sh = (unsigned)((uintptr_t)p & 3) * 8;
+    const unsigned *q = reinterpret_cast<const unsigned *>(p - ((uintptr_t)p & 3));
+    const unsigned w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3);
+    const unsigned w4 = sh ? __ldg(q + 4) : 0u;     // an aligned row needs no fifth word (and it may lie past the image)
+    out = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
   } else {
-    out = 0;
+    unsigned o[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int px = px4 + k;
-      unsigned v = 0;
-      if (px < G.w + 2 * kEdge) v = S[reflect101(px - kEdge, G.w)];
-      out |= v << (8 * k);
+    for (int k = 0; k < 16; k++) {
+      const int px = px16 + k;
+      if (px < G.w + 2 * kEdge) o[k >> 2] |= (unsigned)S[reflect101(px - kEdge, G.w)] << (8 * (k & 3));
     }
+    out = make_uint4(o[0], o[1], o[2], o[3]);
   }
-  uint8_t *D = pyr + G.pyrOffset + (size_t)img * G.planeBytes + (size_t)py * G.pitch + px4;
-  *reinterpret_cast<unsigned *>(D) = out;
+  uint8_t *D = pyr + G.pyrOffset + (size_t)img * G.planeBytes + (size_t)py * G.pitch + px16;
+  *reinterpret_cast<uint4 *>(D) = out;
 }
 
 __global__ void __launch_bounds__(256)
@@ -83,19 +92,25 @@ k_resize_level(const LevelTable *__restrict__ T, uint8_t *__restrict__ pyr, cons
   *reinterpret_cast<unsigned *>(D) = out;
 }
 
-// ---- level l >= 1, fast path: one WARP per 128 x 32 output tile, source window staged by TMA ------------------
-// A lane owns 4 adjacent output columns (one aligned 32-bit store per row) and walks down the tile's rows; the
-// horizontal interpolation of a source row is kept in registers and reused by the next output row whenever both
-// read it (4 of 5 rows at scale 1.2).  Only the interior is produced here (words may spill garbage into the
-// apron bytes next to it); k_fill_borders writes every apron afterwards.
+// ---- level l >= 1, fast path: one WARP per 128 x kRH tile of the PADDED output plane, source window staged by TMA --------
+// A lane owns 4 adjacent output columns (one aligned 32-bit store per row) and walks down the tile's rows.  Columns are
+// padded-plane columns: a lane in the left / right apron maps its columns through reflect-101 to the interior pixel they
+// mirror, i.e. reads the same source pixels as that pixel, so the kernel writes the 19-pixel side aprons itself; only the
+// apron ROWS above / below the interior are left to k_fill_rows.
+// Horizontal pass of one source row: three aligned 32-bit shared-memory loads per lane cover the <= 8 source bytes its four
+// pixels need, two funnel shifts bring them to byte 0, and per pixel one PRMT (lane-constant selector) puts its two source
+// bytes next to each other for one DP2A with the packed (a0, a1) weights: H = S[x0] a0 + S[x0 + 1] a1.  The result is kept
+// as H >> 4 and reused by the next output row whenever both read the source row (4 of 5 rows at scale 1.2).
+// Vertical pass: ((b0 (H0 >> 4)) >> 16) is the high word of (b0 << 16) * (H0 >> 4): one IMAD.HI per term.
 namespace {
 #ifndef ORBGPU_RESIZE_RH
-#define ORBGPU_RESIZE_RH 16
+#define ORBGPU_RESIZE_RH 32
 #endif
 #ifndef ORBGPU_RESIZE_WARPS
 #define ORBGPU_RESIZE_WARPS 4
 #endif
 constexpr int kRW = 128, kRH = ORBGPU_RESIZE_RH, kResizeWarps = ORBGPU_RESIZE_WARPS;
+static_assert(kRH <= 32, "the tile's row table is held one entry per lane");
 
 __global__ void __launch_bounds__(kResizeWarps * 32)
 k_resize_tiles(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict__ T, const int2 *__restrict__ tabs,
@@ -109,12 +124,21 @@ k_resize_tiles(const __grid_constant__ TmaMaps maps, const LevelTable *__restric
   const int level = tile.x;
   const LevelGeom &G = T->lv[level];
   const int img = imgBase + blockIdx.y;
-  const int xp0 = 16 + kRW * tile.y;             // padded column of the tile's first output pixel (4-byte aligned)
+  const int xp = kRW * tile.y + 4 * lane;        // padded column of this lane's first pixel
   const int y0 = kRH * tile.z;                   // interior row of the tile's first output row
-  const int xiFirst = min(max(xp0 - kEdge, 0), G.w - 1);
-  const int sxMin = tabs[G.xTab + xiFirst].x, syMin = tabs[G.yTab + y0].x;
+  const int rows = min(kRH, G.h - y0);
+  // column tables (source x, a0 | a1 << 16) of the lane's four pixels, and the tile's row table (one row per lane)
+  int sx[4], wA[4];
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    const int2 tx = tabs[G.xTab + reflect101(min(xp + p, G.w + 2 * kEdge - 1) - kEdge, G.w)];
+    sx[p] = tx.x; wA[p] = tx.y;
+  }
+  const int2 myRow = tabs[G.yTab + min(y0 + lane, G.h - 1)];
+  const int sxLane = min(min(sx[0], sx[1]), min(sx[2], sx[3]));
+  const int sxMin = __reduce_min_sync(0xffffffffu, sxLane);
+  const int syMin = __shfl_sync(0xffffffffu, myRow.x, 0);
   const int bx = (sxMin + kEdge) & ~15;          // TMA: innermost coordinate on a 16-byte boundary
-  const int lead = sxMin + kEdge - bx;
   uint8_t *slot = smemRaw + ((128u - (smem_u32(smemRaw) & 127u)) & 127u) + warp * slotBytes;
   const int bw = G.rzBoxW;
   if (lane == 0) {
@@ -123,95 +147,78 @@ k_resize_tiles(const __grid_constant__ TmaMaps maps, const LevelTable *__restric
     mbar_expect_tx(&sBar[warp], (unsigned)(G.rzBoxW * G.rzBoxH));
     tma_load_3d(slot, &maps.m[level - 1], bx, syMin + kEdge, img, &sBar[warp]);
   }
-  // per-lane column tables while the copy is in flight
-  const int xp = xp0 + 4 * lane;
-  int rel[4], a0[4], a1[4];
+  // per-lane constants of the horizontal pass: byte offset of the lane's first source pixel in a window row, and per pixel the
+  // PRMT selector that moves its two source bytes (offsets o, o + 1 from that first pixel) into the low half word
+  const int off0 = sxLane + kEdge - bx;
+  const unsigned shift = (unsigned)(off0 & 3) * 8;
+  unsigned sel[4];
 #pragma unroll
-  for (int p = 0; p < 4; p++) {
-    const int xi = min(max(xp + p - kEdge, 0), G.w - 1);
-    const int2 tx = tabs[G.xTab + xi];
-    rel[p] = tx.x - sxMin + lead;
-    a0[p] = tx.y & 0xffff; a1[p] = tx.y >> 16;
-  }
-  const bool colOk = xp + 3 >= kEdge && xp < kEdge + G.w;
+  for (int p = 0; p < 4; p++) { const unsigned o = (unsigned)(sx[p] - sxLane); sel[p] = o | ((o + 1) << 4); }
+  const unsigned *rowWords = reinterpret_cast<const unsigned *>(slot) + (off0 >> 2);
+  const int bwWords = bw >> 2;
+  const bool colOk = xp < G.pitch;
   uint8_t *dst = pyr + G.pyrOffset + (size_t)img * G.planeBytes + (size_t)(y0 + kEdge) * G.pitch + xp;
+  const size_t pitch = (size_t)G.pitch;
   __syncwarp();
   mbar_wait(&sBar[warp], 0);
 
-  int h0[4], h1[4], idx0 = -1, idx1 = -1;
-  const int rows = min(kRH, G.h - y0);
+  auto hpass = [&](int srow, unsigned (&h)[4]) {   // H >> 4 of the lane's four pixels on window row `srow`
+    const unsigned *w = rowWords + srow * bwWords;
+    const unsigned w0 = w[0], w1 = w[1], w2 = w[2];
+    const unsigned a0 = __funnelshift_r(w0, w1, shift), a1 = __funnelshift_r(w1, w2, shift);
+#pragma unroll
+    for (int p = 0; p < 4; p++) h[p] = __dp2a_lo((unsigned)wA[p], __byte_perm(a0, a1, sel[p]), 0u) >> 4;
+  };
+  unsigned hLo[4], hHi[4];
+  int cur = -2;                                    // hLo / hHi hold window rows cur, cur + 1
   for (int r = 0; r < rows; r++) {
-    const int2 ty = tabs[G.yTab + y0 + r];
-    const int s0 = ty.x - syMin, s1 = s0 + 1;    // row s1 has weight 0 when it is clamped in the reference
-    const int b0 = ty.y & 0xffff, b1 = ty.y >> 16;
-    if (s0 == idx1) {
+    const int s0 = __shfl_sync(0xffffffffu, myRow.x, r) - syMin;      // row s0 + 1 has weight 0 where the reference clamps it
+    const unsigned bb = (unsigned)__shfl_sync(0xffffffffu, myRow.y, r);
+    const unsigned b0 = bb << 16, b1 = bb & 0xffff0000u;              // (b0 << 16), (b1 << 16)
+    if (s0 != cur) {
+      if (s0 == cur + 1) {
 #pragma unroll
-      for (int p = 0; p < 4; p++) h0[p] = h1[p];
-      idx0 = idx1;
-    } else if (s0 != idx0) {
-      const uint8_t *S = slot + s0 * bw;
-#pragma unroll
-      for (int p = 0; p < 4; p++) h0[p] = S[rel[p]] * a0[p] + S[rel[p] + 1] * a1[p];
-      idx0 = s0;
+        for (int p = 0; p < 4; p++) hLo[p] = hHi[p];
+      } else {
+        hpass(s0, hLo);
+      }
+      hpass(s0 + 1, hHi);
+      cur = s0;
     }
-    if (s1 != idx1) {
-      const uint8_t *S = slot + s1 * bw;
+    unsigned v[4];
 #pragma unroll
-      for (int p = 0; p < 4; p++) h1[p] = S[rel[p]] * a0[p] + S[rel[p] + 1] * a1[p];
-      idx1 = s1;
-    }
-    unsigned out = 0;
-#pragma unroll
-    for (int p = 0; p < 4; p++)
-      out |= (unsigned)((((b0 * (h0[p] >> 4)) >> 16) + ((b1 * (h1[p] >> 4)) >> 16) + 2) >> 2) << (8 * p);
-    if (colOk) *reinterpret_cast<unsigned *>(dst + (size_t)r * G.pitch) = out;
+    for (int p = 0; p < 4; p++) v[p] = (__umulhi(b0, hLo[p]) + __umulhi(b1, hHi[p]) + 2u) >> 2;
+    const unsigned out = (v[1] * 256u + v[0]) + (v[3] * 256u + v[2]) * 65536u;
+    if (colOk) *reinterpret_cast<unsigned *>(dst + (size_t)r * pitch) = out;
   }
 }
 
-// BORDER_REFLECT_101 apron of levels firstLevel .. nlevels-1 (ORBextractor.cc:1057-1059), one 32-bit word per item:
-// the 19 rows above / below the interior in full, and on interior rows the words covering the left and right aprons.
+// BORDER_REFLECT_101 apron ROWS of levels firstLevel .. nlevels-1 (ORBextractor.cc:1057-1059): the 19 rows above and below the
+// interior are copies of interior rows, side aprons included (k_resize_tiles wrote those), one 128-bit word per thread.
 __global__ void __launch_bounds__(256)
-k_fill_borders(const LevelTable *__restrict__ T, uint8_t *__restrict__ pyr, int firstLevel, int imgBase) {
+k_fill_rows(const LevelTable *__restrict__ T, uint8_t *__restrict__ pyr, int firstLevel, int imgBase) {
   const int level = firstLevel + blockIdx.y, img = imgBase + blockIdx.z;
   const LevelGeom &G = T->lv[level];
   uint8_t *plane = pyr + G.pyrOffset + (size_t)img * G.planeBytes;
-  const int wordsPerRow = G.pitch >> 2;
-  const int leftWords = (kEdge + 3) >> 2;                       // words 0 .. 4 hold padded columns 0 .. 19
-  const int rightFirst = (G.w + kEdge) >> 2;                    // first word touching the right apron
-  const int sideWords = leftWords + (wordsPerRow - rightFirst);
-  const int total = 2 * kEdge * wordsPerRow + G.h * sideWords;
+  const int vecPerRow = G.pitch >> 4;
+  const int total = 2 * kEdge * vecPerRow;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int py, wx;
-    if (i < 2 * kEdge * wordsPerRow) {
-      const int r = i / wordsPerRow;
-      wx = i - r * wordsPerRow;
-      py = r < kEdge ? r : G.h + r;                             // rows 0..18 and h+19 .. h+37
-    } else {
-      const int j = i - 2 * kEdge * wordsPerRow;
-      const int r = j / sideWords, k = j - r * sideWords;
-      py = kEdge + r;
-      wx = k < leftWords ? k : rightFirst + (k - leftWords);
-    }
-    const uint8_t *S = plane + (size_t)(reflect101(py - kEdge, G.h) + kEdge) * G.pitch + kEdge;
-    unsigned out = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int px = 4 * wx + k;
-      if (px < G.w + 2 * kEdge) out |= (unsigned)S[reflect101(px - kEdge, G.w)] << (8 * k);
-    }
-    *reinterpret_cast<unsigned *>(plane + (size_t)py * G.pitch + 4 * wx) = out;
+    const int r = i / vecPerRow, vx = i - r * vecPerRow;
+    const int py = r < kEdge ? r : G.h + r;                           // rows 0 .. 18 and h + 19 .. h + 37
+    const uint4 v = *reinterpret_cast<const uint4 *>(plane + (size_t)(reflect101(py - kEdge, G.h) + kEdge) * G.pitch + 16 * vx);
+    *reinterpret_cast<uint4 *>(plane + (size_t)py * G.pitch + 16 * vx) = v;
   }
 }
 }  // namespace
 
-static dim3 plane_grid(const LevelGeom &G, int batch, dim3 block) {
-  return dim3((G.pitch / 4 + block.x - 1) / block.x, (G.rows + block.y - 1) / block.y, batch);
+static dim3 plane_grid(const LevelGeom &G, int batch, dim3 block, int bytesPerThread = 4) {
+  return dim3((G.pitch / bytesPerThread + block.x - 1) / block.x, (G.rows + block.y - 1) / block.y, batch);
 }
 
 cudaError_t launch_import_level0(const LevelTable &T, const ExtractBuffers &B, const uint8_t *src,
                                  size_t rowStep, size_t imgStep, int imgBase, int batch, cudaStream_t s) {
-  dim3 block(64, 4);
-  k_import_level0<<<plane_grid(T.lv[0], batch, block), block, 0, s>>>(T.lv[0], B.pyr, src, rowStep, imgStep, imgBase);
+  dim3 block(32, 8);
+  k_import_level0<<<plane_grid(T.lv[0], batch, block, 16), block, 0, s>>>(T.lv[0], B.pyr, src, rowStep, imgStep, imgBase);
   count_launch();
   return cudaGetLastError();
 }
@@ -224,13 +231,14 @@ cudaError_t launch_resize_level(const LevelTable &T, const ExtractBuffers &B, in
   return cudaGetLastError();
 }
 
-// TMA box of level `l`'s source window (in level l-1): 128 output columns / 32 output rows worth of source pixels
-// plus the interpolation neighbour, the 16-byte alignment lead and one spare row.
+// TMA box of level `l`'s source window (in level l-1): 128 output columns / kRH output rows worth of source pixels plus the
+// interpolation neighbour, the 16-byte alignment lead, the third word of the last lane's loads and one spare row.
 void resize_box(const LevelTable &T, int l, int *boxW, int *boxH) {
   const LevelGeom &G = T.lv[l], &P = T.lv[l - 1];
   const double sx = (double)P.w / G.w, sy = (double)P.h / G.h;
-  *boxW = ((int)std::ceil((kRW - 1) * sx) + 3 + 15 + 1 + 15) & ~15;
+  *boxW = ((int)std::ceil((kRW - 1) * sx) + 3 + 15 + 12 + 15) & ~15;
   *boxH = (int)std::ceil((kRH - 1) * sy) + 4;
+  if (sx > 2.0 || sy > 2.0) *boxW = *boxH = 1 << 20;                  // the PRMT selectors reach 8 source bytes: generic kernel beyond scale 2
 }
 
 int resize_smem_bytes(const LevelTable &T) {
@@ -246,7 +254,7 @@ cudaError_t resize_configure(int slotBytes) {
 void resize_make_tiles(const LevelTable &T, int level, std::vector<int4> &tiles) {
   tiles.clear();
   const LevelGeom &G = T.lv[level];
-  const int tx = (G.w + 3 + kRW - 1) / kRW, ty = (G.h + kRH - 1) / kRH;
+  const int tx = (G.w + 2 * kEdge + kRW - 1) / kRW, ty = (G.h + kRH - 1) / kRH;     // tiles of the padded width
   for (int y = 0; y < ty; y++)
     for (int x = 0; x < tx; x++) tiles.push_back(make_int4(level, x, y, 0));
 }
@@ -261,8 +269,8 @@ cudaError_t launch_resize_tiles(const LevelTable &T, const ExtractBuffers &B, co
 
 cudaError_t launch_fill_borders(const LevelTable &T, const ExtractBuffers &B, int firstLevel, int imgBase, int batch, cudaStream_t s) {
   if (firstLevel >= T.nlevels) return cudaSuccess;
-  dim3 grid(8, T.nlevels - firstLevel, batch);
-  k_fill_borders<<<grid, 256, 0, s>>>(B.dT, B.pyr, firstLevel, imgBase);
+  dim3 grid(2, T.nlevels - firstLevel, batch);
+  k_fill_rows<<<grid, 256, 0, s>>>(B.dT, B.pyr, firstLevel, imgBase);
   count_launch();
   return cudaGetLastError();
 }

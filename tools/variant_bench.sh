@@ -9,4 +9,4 @@ d=json.loads(sys.stdin.read())
 print('$1', round(d['value']), 'fps', round(d['ms_per_step'],3), 'ms', {k:round(v,3) for k,v in d['stage_ms'].items()})"
 }
 run default | tee "$out"
-for f in gpurun_variants/lib_*.so; do ORBGPU_LIB=$PWD/$f run "$(basename $f)" | tee -a "$out"; done
+for f in $(ls gpurun_variants/lib_*.so 2>/dev/null); do ORBGPU_LIB=$PWD/$f run "$(basename $f)" | tee -a "$out"; done

@@ -10,6 +10,7 @@
 //   H(x)   = S[xo]*a0 + S[xo+1]*a1                      (int32, a0+a1 = 2048)
 //   out    = ((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2
 // with per-axis (offset, coefficient) tables built on the host exactly like OpenCV builds them.
+#include <algorithm>
 #include <cmath>
 
 #include "internal.cuh"
@@ -24,27 +25,29 @@ __device__ __forceinline__ int reflect101(int p, int n) {
   return p >= n ? 2 * (n - 1) - p : p;
 }
 
-// Level 0 = the input image inside its apron.  One thread = 16 padded bytes = one 128-bit store.  Interior chunks gather their
-// 16 source bytes from five aligned 32-bit words re-aligned by funnel shifts (the source rows of a 1241-pixel image start on
-// any byte); chunks that touch the left / right apron take the byte path with the reflect-101 index.
+// Level 0 = the input image inside its apron.  One thread = 16 padded bytes = one 128-bit store.  Two launches of one kernel:
+// BORDER = false covers the chunks that hold interior pixels only — their 16 source bytes come from five aligned 32-bit words
+// re-aligned by funnel shifts (the source rows of a 1241-pixel image start on any byte); BORDER = true covers the few chunks
+// per row that touch the left / right apron (thread = (row, border chunk), every lane on the byte path with the reflect-101
+// index) so that no warp of the bulk copy ever executes the byte loop.
+template <bool BORDER>
 __global__ void __launch_bounds__(256)
 k_import_level0(const __grid_constant__ LevelGeom G, uint8_t *__restrict__ pyr, const uint8_t *__restrict__ src,
-                size_t rowStep, size_t imgStep, int imgBase) {   // level-0 geometry by value: no dependent table loads in front of the copy
+                size_t rowStep, size_t imgStep, int imgBase, int c0, int c1) {   // interior-only chunks are [c0, c1)
   const int img = imgBase + blockIdx.z;
   const int py = blockIdx.y * blockDim.y + threadIdx.y;
-  const int px16 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
-  if (py >= G.rows || px16 >= G.pitch) return;
-  const int sy = reflect101(py - kEdge, G.h);
-  const uint8_t *S = src + (size_t)img * imgStep + (size_t)sy * rowStep;
+  int chunk = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nchunks = G.pitch >> 4;
+  if (BORDER) { if (chunk >= c0) chunk += c1 - c0; } else { chunk += c0; }
+  if (py >= G.rows || chunk >= (BORDER ? nchunks : c1)) return;
+  const int px16 = chunk * 16;
+  const uint8_t *S = src + (size_t)img * imgStep + (size_t)reflect101(py - kEdge, G.h) * rowStep;
   uint4 out;
-  // sixteen interior pixels: no mirroring (the word that holds the chunk's last byte may run 3 bytes past it: on the image's
-  // last row the final chunk takes the byte path instead of reading past the caller's buffer)
-  if (px16 >= kEdge && px16 + 15 < G.w + kEdge && (sy != G.h - 1 || px16 + 19 < G.w + kEdge)) {
+  if (!BORDER) {
     const uint8_t *p = S + (px16 - kEdge);
     const unsigned sh = (unsigned)((uintptr_t)p & 3) * 8;
     const unsigned *q = reinterpret_cast<const unsigned *>(p - ((uintptr_t)p & 3));
-    const unsigned w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3);
-    const unsigned w4 = sh ? __ldg(q + 4) : 0u;     // an aligned row needs no fifth word (and it may lie past the image)
+    const unsigned w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3), w4 = __ldg(q + 4);   // q + 4 holds pixels of this row (see c1)
     out = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
   } else {
     unsigned o[4] = {0u, 0u, 0u, 0u};
@@ -217,8 +220,20 @@ static dim3 plane_grid(const LevelGeom &G, int batch, dim3 block, int bytesPerTh
 
 cudaError_t launch_import_level0(const LevelTable &T, const ExtractBuffers &B, const uint8_t *src,
                                  size_t rowStep, size_t imgStep, int imgBase, int batch, cudaStream_t s) {
+  const LevelGeom &G = T.lv[0];
+  // chunk c (padded bytes 16 c .. 16 c + 15) is interior-only when 16 c >= 19 and 16 c + 15 < w + 19; the bulk path also reads the
+  // aligned word after its last byte, so its last chunk stays 4 pixels short of the row end
+  const int c0 = (kEdge + 15) / 16, c1 = std::max(c0, (G.w + kEdge - 4) / 16), nchunks = G.pitch / 16;
   dim3 block(32, 8);
-  k_import_level0<<<plane_grid(T.lv[0], batch, block, 16), block, 0, s>>>(T.lv[0], B.pyr, src, rowStep, imgStep, imgBase);
+  if (c1 > c0) {
+    dim3 grid((c1 - c0 + block.x - 1) / block.x, (G.rows + block.y - 1) / block.y, batch);
+    k_import_level0<false><<<grid, block, 0, s>>>(G, B.pyr, src, rowStep, imgStep, imgBase, c0, c1);
+    count_launch();
+  }
+  const int nborder = nchunks - (c1 - c0);
+  dim3 bblock(8, 32);
+  dim3 bgrid((nborder + bblock.x - 1) / bblock.x, (G.rows + bblock.y - 1) / bblock.y, batch);
+  k_import_level0<true><<<bgrid, bblock, 0, s>>>(G, B.pyr, src, rowStep, imgStep, imgBase, c0, c1);
   count_launch();
   return cudaGetLastError();
 }

@@ -1,7 +1,11 @@
 // Exercises the shim exactly the way Frame's stereo constructor does (Frame.cc:66-127): two
 // extractor objects, two operator() calls, then stereo matching.  Input: two raw 8-bit images.
 // Output: a binary dump the Python parity test compares with the ctypes path.
-//   shim_demo left.raw right.raw W H nfeatures out.bin
+//   shim_demo left.raw right.raw W H nfeatures out.bin [repeats]
+// With `repeats` it also times the same three calls (the reference's per-frame calling pattern through the C++ drop-in a
+// maintainer links, not through ctypes) with the host pyramid download of mvImagePyramid on and off, and prints one JSON line.
+#include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -44,6 +48,27 @@ int main(int argc, char **argv) {
     for (int y = 0; y < top.rows; y++) fwrite(top.ptr(y), 1, top.cols, f);
     fclose(f);
     printf("shim_demo: %d keypoints, scale[1] = %.7f\n", n, exL.GetScaleFactors()[1]);
+    const int repeats = argc > 7 ? atoi(argv[7]) : 0;
+    if (repeats > 0) {
+      double med[2] = {0, 0};
+      for (int mode = 0; mode < 2; mode++) {                  // 0: mvImagePyramid downloaded every call (default), 1: off
+        exL.SetPyramidDownload(mode == 0); exR.SetPyramidDownload(mode == 0);
+        std::vector<double> ms;
+        for (int i = 0; i < repeats + 5; i++) {
+          const auto t0 = std::chrono::steady_clock::now();
+          exL(imLeft, cv::Mat(), kL, dL);
+          exR(imRight, cv::Mat(), kR, dR);
+          ORB_SLAM2::ComputeStereoMatchesGPU(exL, exR, bf, bf / fx, (int)kL.size(), uR, depth);
+          const auto t1 = std::chrono::steady_clock::now();
+          if (i >= 5) ms.push_back(std::chrono::duration<double, std::milli>(t1 - t0).count());
+        }
+        std::sort(ms.begin(), ms.end());
+        med[mode] = ms[ms.size() / 2];
+      }
+      printf("{\"what\": \"C++ drop-in, one %dx%d stereo frame: ORBextractor::operator() x2 + ComputeStereoMatchesGPU, pageable host buffers\", "
+             "\"keypoints\": %d, \"repeats\": %d, \"ms_with_pyramid_download\": %.4f, \"ms_without_pyramid_download\": %.4f}\n",
+             W, H, n, repeats, med[0], med[1]);
+    }
   } catch (const std::exception &e) {
     fprintf(stderr, "shim_demo: %s\n", e.what());
     return 1;

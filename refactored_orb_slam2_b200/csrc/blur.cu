@@ -6,13 +6,13 @@
 // convolution and any evaluation order reproduces it.  The source plane already carries the
 // reflect-101 apron, so reading 3 px past the interior reproduces the border mode.
 //
-// Work unit = one WARP on a 128 x 64 tile, warps fully independent (no __syncthreads):
-//   * one TMA tensor copy (cp.async.bulk.tensor.3d, per-warp mbarrier) stages the (128+16) x (64+6)
+// Work unit = one WARP on a 128 x 66 tile, warps fully independent (no __syncthreads):
+//   * one TMA tensor copy (cp.async.bulk.tensor.3d, per-warp mbarrier) stages the (128+16) x (66+6)
 //     source window in the warp's shared-memory slot;
-//   * a lane owns 4 adjacent columns and walks down the rows: 3 LDS.32 per row, horizontal taps on
-//     byte pairs packed 16x2 (one IMAD filters two pixels; sums <= 65280 never carry across halves),
-//     then 7 rolling 32-bit accumulators per column take the vertical taps; every input row
-//     finishes one output row, which leaves as one 32-bit store per lane.
+//   * a lane owns 4 adjacent columns and walks down the rows: 3 LDS.32 per row, per pixel two funnel-shifted
+//     words and two DP4A for the seven horizontal taps (sums <= 65280 fit 16 bits),
+//     then the vertical taps run as IDP.2A on vertically packed row pairs (see the kernel); every input
+//     row finishes one output row, which leaves as one 32-bit store per lane.
 // Tiles are anchored at padded x = 4: the window then starts on a 16-byte boundary (a TMA
 // requirement for the innermost coordinate) and loads / stores are 4-byte aligned; the 15 columns
 // left of the interior receive valid blur values of the mirrored image and are never read.
@@ -24,7 +24,7 @@ namespace orbgpu {
 namespace {
 
 #ifndef ORBGPU_BLUR_TH
-#define ORBGPU_BLUR_TH 64
+#define ORBGPU_BLUR_TH 66
 #endif
 #ifndef ORBGPU_BLUR_WARPS
 #define ORBGPU_BLUR_WARPS 4
@@ -33,17 +33,6 @@ constexpr int kTW = 128, kTH = ORBGPU_BLUR_TH;
 constexpr int kBoxW = kTW + 16, kBoxH = kTH + 6;
 constexpr int kWarpsPerCta = ORBGPU_BLUR_WARPS;
 constexpr int kSlotBytes = (kBoxW * kBoxH + 127) & ~127;
-
-// bytes O, O+1 of the 12-byte window (w0, w1, w2) zero-extended into packed 16x2
-template <int O>
-__device__ __forceinline__ unsigned pair_at(unsigned w0, unsigned w1, unsigned w2) {
-  static_assert(O >= 0 && O <= 10, "window offset");
-  if constexpr (O <= 2) return __byte_perm(w0, 0u, 0x4040u | O | ((O + 1) << 8));
-  else if constexpr (O == 3) return __byte_perm(w0, w1, 0x4443u) & 0x00ff00ffu;
-  else if constexpr (O <= 6) return __byte_perm(w1, 0u, 0x4040u | (O - 4) | ((O - 3) << 8));
-  else if constexpr (O == 7) return __byte_perm(w1, w2, 0x4443u) & 0x00ff00ffu;
-  else return __byte_perm(w2, 0u, 0x4040u | (O - 8) | ((O - 7) << 8));
-}
 
 // tiles[t] = (level, tile x, tile y, 0)
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
@@ -76,44 +65,55 @@ k_blur(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict__ T, c
   const bool colOk = x < xEnd;
   uint8_t *dst = blur + G.pyrOffset + (size_t)img * G.planeBytes + (size_t)y0 * G.pitch + x;
 
-  unsigned acc[7][4];
+  // Vertical pass on VERTICALLY packed pairs: P(r)[p] = (h of pixel p on input row r-1, h on input row r) as two 16-bit halves,
+  // so that one IDP.2A applies two vertical taps of one pixel.  The output row centred on input row r-3 is complete when input
+  // row r arrives:
+  //   18 h[r-6] + 34 h[r-5] | 48 h[r-4] + 56 h[r-3] | 48 h[r-2] + 34 h[r-1] | 18 h[r]
+  //   = dp2a(P(r-5), 18, 34) + dp2a(P(r-3), 48, 56) + dp2a(P(r-1), 48, 34) + dp2a(P(r), 0, 18)      (+ 0x8000, then >> 16)
+  // Six rows of pairs (24 registers, rotated by the six-fold unroll) replace the seven rolling 32-bit accumulators: per row and
+  // lane 4 PRMT + 16 IDP.2A + 3 PRMT (byte 2 of each sum IS the rounded result) instead of 4 extractions + 28 IMAD + 11.
+  unsigned P[6][4];
+  unsigned hPrev[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-  for (int j = 0; j < 7; j++)
+  for (int k = 0; k < 6; k++)
 #pragma unroll
-    for (int p = 0; p < 4; p++) acc[j][p] = 0;
+    for (int p = 0; p < 4; p++) P[k][p] = 0u;
 
-  // 7 input rows per loop trip: the accumulator rotation has period 7, so registers stay static while the code stays
-  // small enough for the instruction cache (a full 70-row unroll stalled on instruction fetch)
-  static_assert(kBoxH % 7 == 0, "row loop is unrolled by the accumulator period");
-  for (int r0 = 0; r0 < kBoxH; r0 += 7) {
+  static_assert(kBoxH % 6 == 0, "row loop is unrolled by the pair-history depth");
+  for (int r0 = 0; r0 < kBoxH; r0 += 6) {
 #pragma unroll
-    for (int rr = 0; rr < 7; rr++) {
+    for (int rr = 0; rr < 6; rr++) {
       const int r = r0 + rr;
       // horizontal taps of input row r (tile row r-3): h for pixels x..x+3, two pixels per register
       const unsigned *row = reinterpret_cast<const unsigned *>(slot + r * kBoxW) + lane;
       const unsigned w0 = row[0], w1 = row[1], w2 = row[2];
-      const unsigned p1 = pair_at<1>(w0, w1, w2), p2 = pair_at<2>(w0, w1, w2), p3 = pair_at<3>(w0, w1, w2),
-                     p4 = pair_at<4>(w0, w1, w2), p5 = pair_at<5>(w0, w1, w2), p6 = pair_at<6>(w0, w1, w2),
-                     p7 = pair_at<7>(w0, w1, w2), p8 = pair_at<8>(w0, w1, w2), p9 = pair_at<9>(w0, w1, w2);
-      // pixel pair (x, x+1): window bytes 1..8 ; pair (x+2, x+3): bytes 3..10
-      const unsigned hA = 18u * (p1 + p7) + 34u * (p2 + p6) + 48u * (p3 + p5) + 56u * p4;
-      const unsigned hB = 18u * (p3 + p9) + 34u * (p4 + p8) + 48u * (p5 + p7) + 56u * p6;
-      const unsigned h[4] = {hA & 0xffffu, hA >> 16, hB & 0xffffu, hB >> 16};
-      // vertical taps: input row r feeds output rows r-6 .. r; accumulator (rr + j) % 7 belongs to output row r-6+j
-      constexpr unsigned kW[7] = {18u, 34u, 48u, 56u, 48u, 34u, 18u};
+      // pixel x+j reads window bytes j+1 .. j+7 (w0 = bytes x-4 .. x-1): two funnel-shifted words per pixel hold them, and the
+      // seven taps are two byte dot products  dp4a(bytes j+1..j+4, 18 34 48 56) + dp4a(bytes j+5..j+8, 48 34 18 0)
+      unsigned h[4];
 #pragma unroll
-      for (int j = 0; j < 7; j++)
+      for (int j = 0; j < 4; j++) {
+        const unsigned a = j == 3 ? w1 : __funnelshift_r(w0, w1, 8 * (j + 1));
+        const unsigned b = j == 3 ? w2 : __funnelshift_r(w1, w2, 8 * (j + 1));
+        h[j] = __dp4a(b, 0x00122230u, __dp4a(a, 0x38302212u, 0u));
+      }
+      unsigned (&Pn)[4] = P[rr];                         // P(r) takes the slot of P(r-6)
 #pragma unroll
-        for (int p = 0; p < 4; p++) acc[(rr + j) % 7][p] += kW[6 - j] * h[p];
-      // accumulator rr now holds output row r-6 complete
+      for (int j = 0; j < 4; j++) { Pn[j] = __byte_perm(hPrev[j], h[j], 0x5410u); hPrev[j] = h[j]; }
       const int orow = r - 6;
       if (orow >= 0 && colOk && orow < rowsOut) {
-        const unsigned out = ((acc[rr][0] + 0x8000u) >> 16) | (((acc[rr][1] + 0x8000u) >> 16) << 8) |
-                             (((acc[rr][2] + 0x8000u) >> 16) << 16) | (((acc[rr][3] + 0x8000u) >> 16) << 24);
-        *reinterpret_cast<unsigned *>(dst + (size_t)orow * G.pitch) = out;
-      }
+        const unsigned (&P1)[4] = P[(rr + 5) % 6], (&P3)[4] = P[(rr + 3) % 6], (&P5)[4] = P[(rr + 1) % 6];
+        unsigned sum[4];
 #pragma unroll
-      for (int p = 0; p < 4; p++) acc[rr][p] = 0;       // it restarts as the accumulator of output row r+1
+        for (int p = 0; p < 4; p++) {
+          unsigned a = __dp2a_lo(P5[p], 0x00002212u, 0x8000u);             // 18 h[r-6] + 34 h[r-5] + rounding
+          a = __dp2a_lo(P3[p], 0x00003830u, a);                            // 48 h[r-4] + 56 h[r-3]
+          a = __dp2a_lo(P1[p], 0x00002230u, a);                            // 48 h[r-2] + 34 h[r-1]
+          sum[p] = __dp2a_lo(Pn[p], 0x00001200u, a);                       //  0 h[r-1] + 18 h[r]
+        }
+        // (sum >> 16) fits a byte: byte 2 of each sum, packed
+        const unsigned lo = __byte_perm(sum[0], sum[1], 0x0062u), hi = __byte_perm(sum[2], sum[3], 0x0062u);
+        *reinterpret_cast<unsigned *>(dst + (size_t)orow * G.pitch) = __byte_perm(lo, hi, 0x5410u);
+      }
     }
   }
 }

@@ -107,7 +107,7 @@ k_resize_level(const LevelTable *__restrict__ T, uint8_t *__restrict__ pyr, cons
 // Vertical pass: ((b0 (H0 >> 4)) >> 16) is the high word of (b0 << 16) * (H0 >> 4): one IMAD.HI per term.
 namespace {
 #ifndef ORBGPU_RESIZE_RH
-#define ORBGPU_RESIZE_RH 32
+#define ORBGPU_RESIZE_RH 24
 #endif
 #ifndef ORBGPU_RESIZE_WARPS
 #define ORBGPU_RESIZE_WARPS 4

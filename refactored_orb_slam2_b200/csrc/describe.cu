@@ -128,13 +128,18 @@ k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, co
   const int img = imgBase + blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int slot = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);      // output row of this warp's keypoint
-  const int *cnt = selCount + img * kMaxLevels;
-  int level = 0, start = 0, total = 0;
-  for (int l = 0; l < T->nlevels; l++) {
-    const int c = cnt[l];
-    if (slot >= total + c) { level = l + 1; start = total + c; }
-    total += c;
+  // the image's output rows are level-major: lane l holds the end (exclusive) of level l's rows after a warp scan of the
+  // per-level octree counts; the keypoint's level is the number of levels that end at or before its slot
+  const int nlevels = T->nlevels;
+  int levelEnd = lane < nlevels ? selCount[img * kMaxLevels + lane] : 0;
+#pragma unroll
+  for (int o = 1; o < kMaxLevels; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, levelEnd, o);
+    if (lane >= o) levelEnd += v;
   }
+  const int total = __shfl_sync(0xffffffffu, levelEnd, nlevels - 1);
+  const int level = min(__popc(__ballot_sync(0xffffffffu, lane < nlevels && slot >= levelEnd)), nlevels - 1);
+  const int start = level ? __shfl_sync(0xffffffffu, levelEnd, level - 1) : 0;
   const int kpCap = T->kpCap;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     kpCount[img] = min(total, kpCap);

@@ -70,7 +70,7 @@ struct orbgpu_extractor {
   int2 *dTabs = nullptr; size_t tabsCap = 0;
   int4 *dTiles = nullptr; size_t tilesCap = 0; int ntiles = 0;
   FastConfig fastCfg{};
-  TmaMaps blurMaps{}, rzMaps{};
+  TmaMaps blurMaps{}, rzMaps{}, descDiscMaps{}, descPatchMaps{};
   int4 *dRzTiles = nullptr; size_t rzTilesCap = 0; int rzTileOff[kMaxLevels] = {}, rzTileCnt[kMaxLevels] = {};
   int rzSlotBytes = 0;
   int4 *dBlurTiles = nullptr; size_t blurTilesCap = 0; int nBlurTiles = 0;
@@ -276,6 +276,18 @@ int configure(orbgpu_extractor *e, int w, int h) {
     ORBGPU_CUDA_CHECK(encode_plane_map(&blurMaps.m[l], e->dPyr + G.pyrOffset, G.pitch, G.rows, G.planeBytes, e->p.max_batch,
                                        blur_box_w(), blur_box_h()));
   }
+  TmaMaps discMaps, patchMaps;         // describe: 48 x 31 boxes on the pyramid levels, 64 x 37 boxes on the blurred levels
+  {
+    int dw, dh, pw, ph;
+    describe_boxes(&dw, &dh, &pw, &ph);
+    for (int l = 0; l < T.nlevels; l++) {
+      const LevelGeom &G = T.lv[l];
+      ORBGPU_CUDA_CHECK(encode_plane_map(&discMaps.m[l], e->dPyr + G.pyrOffset, G.pitch, G.rows, G.planeBytes, e->p.max_batch, dw, dh));
+      ORBGPU_CUDA_CHECK(encode_plane_map(&patchMaps.m[l], e->dBlur + G.pyrOffset, G.pitch, G.rows, G.planeBytes, e->p.max_batch, pw, ph));
+    }
+    ORBGPU_CUDA_CHECK(describe_configure());
+    ORBGPU_CUDA_CHECK(describe_configure_lat());
+  }
   if (blurTiles.size() > e->blurTilesCap) {
     if (e->dBlurTiles) cudaFree(e->dBlurTiles);
     e->blurTilesCap = blurTiles.size() + 64;
@@ -307,6 +319,7 @@ int configure(orbgpu_extractor *e, int w, int h) {
   }
   e->T = T; e->ntiles = (int)tiles.size(); e->fastCfg = fc; e->octSmem = octSmem;
   e->blurMaps = blurMaps; e->nBlurTiles = (int)blurTiles.size();
+  e->descDiscMaps = discMaps; e->descPatchMaps = patchMaps;
   e->rzMaps = rzMaps; e->rzSlotBytes = rzSlot;
   for (int l = 0; l < kMaxLevels; l++) { e->rzTileOff[l] = rzOff[l]; e->rzTileCnt[l] = rzCnt[l]; }
   e->cfgW = w; e->cfgH = h;
@@ -357,7 +370,7 @@ int run_extract_range(orbgpu_extractor *e, const uint8_t *dImages, int imgBase, 
     ORBGPU_CUDA_CHECK(launch_blur(e->T, B, e->blurMaps, e->dBlurTiles, e->nBlurTiles, imgBase, batch, e->side));
     ORBGPU_CUDA_CHECK(cudaEventRecord(e->evJoin, e->side));
     ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(s, e->evJoin, 0));
-    ORBGPU_CUDA_CHECK(lat ? launch_describe_lat(e->T, B, imgBase, batch, s) : launch_describe(e->T, B, imgBase, batch, s));
+    ORBGPU_CUDA_CHECK(lat ? launch_describe_lat(e->T, B, e->descDiscMaps, e->descPatchMaps, imgBase, batch, s) : launch_describe(e->T, B, e->descDiscMaps, e->descPatchMaps, imgBase, batch, s));
     return ORBGPU_OK;
   }
   {
@@ -369,7 +382,7 @@ int run_extract_range(orbgpu_extractor *e, const uint8_t *dImages, int imgBase, 
   { StageTimer t(e, 1); ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->dTiles, e->ntiles, e->fastCfg, imgBase, batch, s)); }
   { StageTimer t(e, 2); ORBGPU_CUDA_CHECK(lat ? launch_octree_lat(e->T, B, imgBase, batch, e->octSmem, s) : launch_octree(e->T, B, imgBase, batch, e->octSmem, s)); }
   { StageTimer t(e, 3); ORBGPU_CUDA_CHECK(launch_blur(e->T, B, e->blurMaps, e->dBlurTiles, e->nBlurTiles, imgBase, batch, s)); }
-  { StageTimer t(e, 4); ORBGPU_CUDA_CHECK(lat ? launch_describe_lat(e->T, B, imgBase, batch, s) : launch_describe(e->T, B, imgBase, batch, s)); }
+  { StageTimer t(e, 4); ORBGPU_CUDA_CHECK(lat ? launch_describe_lat(e->T, B, e->descDiscMaps, e->descPatchMaps, imgBase, batch, s) : launch_describe(e->T, B, e->descDiscMaps, e->descPatchMaps, imgBase, batch, s)); }
   return ORBGPU_OK;
 }
 

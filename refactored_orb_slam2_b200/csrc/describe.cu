@@ -3,12 +3,12 @@
 // tail of ORBextractor::operator() (ORBextractor.cc:1023-1037).
 //
 // One warp = one keypoint.
-//  * IC_Angle: 31 coalesced row reads of the UNBLURRED level (lane = column u), integer moments
+//  * IC_Angle: 31 row reads of the staged disc of the UNBLURRED level (lane = column u, immediate offsets), integer moments
 //    m10 / m01 reduced by shuffles (exact, order-free), then cv::fastAtan2's float polynomial with
 //    round-to-nearest mul/add/div intrinsics (the reference build never fuses into FMAs).
-//  * rBRIEF: the 37 x 37 blurred patch around the keypoint (pattern reach <= 18 px) is first staged in
-//    the warp's shared-memory slot with coalesced 32-bit row loads — the 512 rotated sample positions
-//    are a scatter that would otherwise cost one 32-byte L2 sector per sample; then lane i builds
+//  * both neighbourhoods are staged in the warp's shared-memory slot by TWO TMA tensor copies per keypoint (the 31 x 31
+//    orientation disc from the level, the 37 x 37 patch from its blurred copy; pattern reach <= 18 px) — the 512 rotated
+//    sample positions are a scatter that would otherwise cost one 32-byte L2 sector per sample; then lane i builds
 //    descriptor byte i from 16 pattern points rotated by (cos, sin) of the angle.  cosf/sinf replicate glibc's double-precision sincosf algorithm (see sincos_glibc) so
 //    that cvRound(x*b + y*a) lands on the same pixel as on the host.
 //  * The keypoint record (cv::KeyPoint layout) and the 32-byte descriptor row go straight to their
@@ -16,6 +16,7 @@
 #include <mutex>
 
 #include "internal.cuh"
+#include "tma.cuh"
 
 namespace orbgpu {
 
@@ -115,19 +116,26 @@ __device__ __forceinline__ void sincos_glibc(float y, float *sinp, float *cosp) 
 constexpr int kWarpsPerCta = ORBGPU_DESCRIBE_WARPS;
 constexpr int kPatchR = 18;                    // |rotated pattern coordinate| <= round(13 * sqrt 2) = 18 < EDGE_THRESHOLD
 constexpr int kPatchRows = 2 * kPatchR + 1;    // 37
-constexpr int kPatchWords = 10;                // 40 bytes per staged row: up to 3 alignment bytes + 37
-constexpr int kPatchIters = (kPatchRows + 2) / 3;   // three rows of 10 words per warp-wide load
+// Both neighbourhoods of a keypoint arrive as TMA boxes (cp.async.bulk.tensor.3d on the level's [batch][rows][pitch] maps,
+// one per-warp mbarrier): the 31 x 31 orientation disc from the pyramid level and the 37 x 37 patch from the blurred level.
+// Box columns start on the 16-byte boundary at or before the first needed pixel, so the boxes are 48 and 64 bytes wide.
+constexpr int kDiscW = 48, kDiscRows = 2 * kHalfPatch + 1;        // 15 alignment bytes + 31 <= 48
+constexpr int kPatchW = 64;                                        // 15 alignment bytes + 37 <= 64
+constexpr int kDiscBytes = kDiscW * kDiscRows, kPatchBytes = kPatchW * kPatchRows;
+constexpr int kDiscSlot = (kDiscBytes + 127) & ~127, kPatchSlot = (kPatchBytes + 127) & ~127;
+constexpr int kWarpSlot = kDiscSlot + kPatchSlot;
 
-// blockIdx.x = chunk of 8 output slots (level-major keypoint index), blockIdx.y = image
+// blockIdx.x = chunk of kWarpsPerCta output slots (level-major keypoint index), blockIdx.y = image
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur,
+k_describe(const __grid_constant__ TmaMaps pyrMaps, const __grid_constant__ TmaMaps blurMaps, const LevelTable *__restrict__ T,
            const int4 *__restrict__ selAll, const int *__restrict__ selCount, orbgpu_keypoint *__restrict__ kps,
            uint8_t *__restrict__ desc, int *__restrict__ kpCount, unsigned *__restrict__ status, int imgBase) {
-  __shared__ __align__(16) unsigned sPatch[kWarpsPerCta][kPatchRows * kPatchWords];
+  extern __shared__ uint8_t smemRaw[];
+  __shared__ __align__(8) unsigned long long sBar[kWarpsPerCta];
 
   const int img = imgBase + blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int slot = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);      // output row of this warp's keypoint
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slot = blockIdx.x * kWarpsPerCta + warp;                    // output row of this warp's keypoint
   // the image's output rows are level-major: lane l holds the end (exclusive) of level l's rows after a warp scan of the
   // per-level octree counts; the keypoint's level is the number of levels that end at or before its slot
   const int nlevels = T->nlevels;
@@ -147,37 +155,34 @@ k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, co
   }
   if (slot >= total || slot >= kpCap) return;
   const LevelGeom &G = T->lv[level];
-  const int pitch = G.pitch;
-
   const int4 s = selAll[G.selOffset + (size_t)img * G.selCap + (slot - start)];   // x_level, y_level, response
-  const size_t plane = G.pyrOffset + (size_t)img * G.planeBytes;
 
-  // ---- every global load of this keypoint is issued up front (31 orientation rows + 13 patch words per lane), so a
-  // warp pays one memory latency instead of one per row
+  // ---- stage both neighbourhoods: two tensor copies per keypoint, no per-row address arithmetic, one memory latency
+  uint8_t *disc = smemRaw + ((128u - (smem_u32(smemRaw) & 127u)) & 127u) + warp * kWarpSlot;
+  uint8_t *patch = disc + kDiscSlot;
+  const int dx0 = s.x + kEdge - kHalfPatch, px0 = s.x + kEdge - kPatchR;      // padded columns of u = -15 / of the patch's first pixel
+  if (lane == 0) {
+    mbar_init(&sBar[warp], 1);
+    mbar_fence_init();
+    mbar_expect_tx(&sBar[warp], kDiscBytes + kPatchBytes);
+    tma_load_3d(disc, &pyrMaps.m[level], dx0 & ~15, s.y + kEdge - kHalfPatch, img, &sBar[warp]);
+    tma_load_3d(patch, &blurMaps.m[level], px0 & ~15, s.y + kEdge - kPatchR, img, &sBar[warp]);
+  }
+  __syncwarp();
   static constexpr int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};   // ORBextractor.cc:449-463
   const int u = lane - kHalfPatch;
   const int au = abs(u);
+  mbar_wait(&sBar[warp], 0);
   int ring[2 * kHalfPatch + 1];
   {
-    const uint8_t *rp = pyr + plane + (size_t)(s.y + kEdge - kHalfPatch) * pitch + (s.x + kEdge + u);
+    const uint8_t *rp = disc + (dx0 & 15) + min(lane, 2 * kHalfPatch);     // lane = column u + 15 (lane 31 idle)
 #pragma unroll
-    for (int i = 0; i <= 2 * kHalfPatch; i++, rp += pitch) {
+    for (int i = 0; i <= 2 * kHalfPatch; i++) {
       const int v = i - kHalfPatch;
-      ring[i] = (lane < 31 && au <= kUmax[v < 0 ? -v : v]) ? (int)*rp : 0;
+      ring[i] = (lane < 31 && au <= kUmax[v < 0 ? -v : v]) ? (int)rp[i * kDiscW] : 0;
     }
   }
-  // blurred patch: rows y-18 .. y+18, from the 4-byte aligned column at or before x-18; a warp-wide load covers 3 rows
-  unsigned *patch = sPatch[threadIdx.x >> 5];
-  const int px0 = s.x + kEdge - kPatchR;                       // padded column of the patch's first pixel
-  const int lead = px0 & 3;
-  const int sub = lane / kPatchWords, word = lane - sub * kPatchWords;   // lanes 30, 31 idle
-  unsigned pw[kPatchIters];
-  {
-    const uint8_t *pp = blur + plane + (size_t)(s.y + kEdge - kPatchR + sub) * pitch + (px0 - lead) + 4 * word;
-#pragma unroll
-    for (int k = 0; k < kPatchIters; k++, pp += 3 * pitch)
-      pw[k] = (sub < 3 && 3 * k + sub < kPatchRows) ? *reinterpret_cast<const unsigned *>(pp) : 0u;
-  }
+  const int lead = px0 & 15;
 
   // ---- IC_Angle
   int m10 = 0, m01 = 0;
@@ -198,15 +203,11 @@ k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, co
   const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
   float a, b;
   sincos_glibc(__fmul_rn(angle, factorPI), &b, &a);   // a = cos, b = sin
-#pragma unroll
-  for (int k = 0; k < kPatchIters; k++)
-    if (sub < 3 && 3 * k + sub < kPatchRows) patch[(3 * k + sub) * kPatchWords + word] = pw[k];
-  __syncwarp();
   // cvRound(x) = round-half-even = the low mantissa bits of x + 1.5 * 2^23 for |x| < 2^22 (an FADD on the FMA pipe instead of
   // an F2I on the quarter-rate XU pipe); the two biases are folded into the base offset (bits of 1.5 * 2^23 = 0x4B400000)
   const float kMagic = 12582912.0f;
-  const uint8_t *pb = reinterpret_cast<const uint8_t *>(patch);
-  const unsigned off0 = (unsigned)(kPatchR * (kPatchWords * 4) + lead + kPatchR) - 0x4B400000u * (unsigned)(kPatchWords * 4 + 1);   // mod 2^32
+  const uint8_t *pb = patch;
+  const unsigned off0 = (unsigned)(kPatchR * kPatchW + lead + kPatchR) - 0x4B400000u * (unsigned)(kPatchW + 1);   // mod 2^32
   const float2 *p = d_patternT + lane;         // point 16*lane + j sits at p[32 * j]
   unsigned val = 0;
 #pragma unroll
@@ -217,7 +218,7 @@ k_describe(const LevelTable *__restrict__ T, const uint8_t *__restrict__ pyr, co
       const float2 q = __ldg(&p[32 * (2 * bit + e)]);
       const unsigned ry = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(q.x, b), __fmul_rn(q.y, a)), kMagic));
       const unsigned rx = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(q.x, a), __fmul_rn(q.y, b)), kMagic));
-      t[e] = pb[ry * (unsigned)(kPatchWords * 4) + rx + off0];
+      t[e] = pb[ry * (unsigned)kPatchW + rx + off0];
     }
     val |= (unsigned)(t[0] < t[1]) << bit;
   }
@@ -297,12 +298,22 @@ cudaError_t VNAME(describe_prepare)() {
   return e;
 }
 
-cudaError_t VNAME(launch_describe)(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, cudaStream_t s) {
+int VNAME(describe_smem_bytes)() { return 128 + kWarpsPerCta * kWarpSlot; }
+cudaError_t VNAME(describe_configure)() {
+  return cudaFuncSetAttribute(k_describe, cudaFuncAttributeMaxDynamicSharedMemorySize, VNAME(describe_smem_bytes)());
+}
+
+cudaError_t VNAME(launch_describe)(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &pyrMaps, const TmaMaps &blurMaps, int imgBase,
+                                   int batch, cudaStream_t s) {
   dim3 grid((T.kpCap + kWarpsPerCta - 1) / kWarpsPerCta, batch);
-  k_describe<<<grid, kWarpsPerCta * 32, 0, s>>>(B.dT, B.pyr, B.blur, B.sel, B.selCount, B.kps, B.desc, B.kpCount,
-                                                B.status, imgBase);
+  k_describe<<<grid, kWarpsPerCta * 32, VNAME(describe_smem_bytes)(), s>>>(pyrMaps, blurMaps, B.dT, B.sel, B.selCount, B.kps, B.desc, B.kpCount,
+                                                                          B.status, imgBase);
   count_launch();
   return cudaGetLastError();
 }
+
+#ifndef ORBGPU_VARIANT_IS_SECONDARY
+void describe_boxes(int *discW, int *discH, int *patchW, int *patchH) { *discW = kDiscW; *discH = kDiscRows; *patchW = kPatchW; *patchH = kPatchRows; }
+#endif
 
 }  // namespace orbgpu

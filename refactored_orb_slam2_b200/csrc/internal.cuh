@@ -137,7 +137,11 @@ cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const int4
 cudaError_t launch_octree(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, int smemBytes,
                           cudaStream_t s);
 int hamming_dense_q(int nq);
-cudaError_t launch_describe(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, cudaStream_t s);
+cudaError_t launch_describe(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &pyrMaps, const TmaMaps &blurMaps, int imgBase, int batch,
+                            cudaStream_t s);
+cudaError_t describe_configure();
+cudaError_t describe_configure_lat();
+void describe_boxes(int *discW, int *discH, int *patchW, int *patchH);   // TMA boxes of the two staged neighbourhoods
 cudaError_t launch_sincos_checksum(unsigned firstBits, unsigned long long count, int chunkLog2, unsigned long long *dSums, cudaStream_t s);
 cudaError_t launch_sincos_values(unsigned firstBits, int n, float *dS, float *dC, cudaStream_t s);
 cudaError_t describe_prepare();       // pattern table of the variant, once per device, outside stream capture
@@ -146,7 +150,8 @@ cudaError_t describe_prepare_lat();
 constexpr int kLatencyBatch = 16;
 cudaError_t launch_octree_lat(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, int smemBytes, cudaStream_t s);
 cudaError_t octree_configure_lat(int smemBytes);
-cudaError_t launch_describe_lat(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, cudaStream_t s);
+cudaError_t launch_describe_lat(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &pyrMaps, const TmaMaps &blurMaps, int imgBase, int batch,
+                                cudaStream_t s);
 size_t octree_smem_bytes(int maxNodes);
 cudaError_t octree_configure(int smemBytes);
 cudaError_t fast_configure(int smemBytes);

@@ -84,7 +84,10 @@ k_stereo_rows(StereoArgs A, int rows) {
   }
 }
 
-__global__ void __launch_bounds__(kWarps * 32)
+#ifndef ORBGPU_STEREO_MIN_CTAS
+#define ORBGPU_STEREO_MIN_CTAS 24     // 40 registers: the kernel is latency bound, 48 instead of 36 resident warps (0.64 -> 0.59 ms per 320 pairs)
+#endif
+__global__ void __launch_bounds__(kWarps * 32, ORBGPU_STEREO_MIN_CTAS)
 k_stereo_match(const LevelTable *__restrict__ T, StereoArgs A, int rows, int rowReach) {
   const int pair = blockIdx.y;
   const int lane = threadIdx.x & 31;

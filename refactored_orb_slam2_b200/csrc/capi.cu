@@ -68,7 +68,7 @@ struct orbgpu_extractor {
   LevelTable T{};
   LevelTable *dT = nullptr;
   int2 *dTabs = nullptr; size_t tabsCap = 0;
-  int4 *dTiles = nullptr; size_t tilesCap = 0; int ntiles = 0;
+  int4 *dTiles = nullptr; size_t tilesCap = 0; int ntiles = 0, ntilesShift = 0;   // FAST strips: ntiles plain ones, then ntilesShift shifted ones
   FastConfig fastCfg{};
   TmaMaps blurMaps{}, rzMaps{}, descDiscMaps{}, descPatchMaps{};
   int4 *dRzTiles = nullptr; size_t rzTilesCap = 0; int rzTileOff[kMaxLevels] = {}, rzTileCnt[kMaxLevels] = {};
@@ -240,6 +240,9 @@ int configure(orbgpu_extractor *e, int w, int h) {
       set_error("internal: FAST cell %dx%d does not fit a strip", T.lv[l].wCell, T.lv[l].hCell);
       return ORBGPU_E_UNSUPPORTED;
     }
+  // FAST strips that run in the shifted form go to the end of the list: they are a launch of their own
+  const int nPlainStrips = (int)(std::stable_partition(tiles.begin(), tiles.end(), [&](const int4 &t) { return !fast_strip_shifted(T.lv[t.x], t.z, t.w); }) -
+                                 tiles.begin());
   ORBGPU_CUDA_CHECK(cudaStreamSynchronize(e->stream));
   if (tabs.size() > e->tabsCap) {
     if (e->dTabs) cudaFree(e->dTabs);
@@ -317,7 +320,7 @@ int configure(orbgpu_extractor *e, int w, int h) {
     ORBGPU_CUDA_CHECK(octree_configure_lat(octMax[d]));
     ORBGPU_CUDA_CHECK(fast_configure(fastMax[d]));
   }
-  e->T = T; e->ntiles = (int)tiles.size(); e->fastCfg = fc; e->octSmem = octSmem;
+  e->T = T; e->ntiles = nPlainStrips; e->ntilesShift = (int)tiles.size() - nPlainStrips; e->fastCfg = fc; e->octSmem = octSmem;
   e->blurMaps = blurMaps; e->nBlurTiles = (int)blurTiles.size();
   e->descDiscMaps = discMaps; e->descPatchMaps = patchMaps;
   e->rzMaps = rzMaps; e->rzSlotBytes = rzSlot;
@@ -363,7 +366,7 @@ int run_extract_range(orbgpu_extractor *e, const uint8_t *dImages, int imgBase, 
     ORBGPU_CUDA_CHECK(launch_import_level0(e->T, B, dImages, rowStep, imgStep, imgBase, batch, s));
     int rc = pyramid_rest(s);
     if (rc) return rc;
-    ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->dTiles, e->ntiles, e->fastCfg, imgBase, batch, s));
+    ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->dTiles, e->ntiles, e->ntilesShift, e->fastCfg, imgBase, batch, s));
     ORBGPU_CUDA_CHECK(cudaEventRecord(e->evFork, s));
     ORBGPU_CUDA_CHECK(lat ? launch_octree_lat(e->T, B, imgBase, batch, e->octSmem, s) : launch_octree(e->T, B, imgBase, batch, e->octSmem, s));
     ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(e->side, e->evFork, 0));     // the octree's CTAs are placed first, the blur fills the rest
@@ -379,7 +382,7 @@ int run_extract_range(orbgpu_extractor *e, const uint8_t *dImages, int imgBase, 
     int rc = pyramid_rest(s);
     if (rc) return rc;
   }
-  { StageTimer t(e, 1); ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->dTiles, e->ntiles, e->fastCfg, imgBase, batch, s)); }
+  { StageTimer t(e, 1); ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->dTiles, e->ntiles, e->ntilesShift, e->fastCfg, imgBase, batch, s)); }
   { StageTimer t(e, 2); ORBGPU_CUDA_CHECK(lat ? launch_octree_lat(e->T, B, imgBase, batch, e->octSmem, s) : launch_octree(e->T, B, imgBase, batch, e->octSmem, s)); }
   { StageTimer t(e, 3); ORBGPU_CUDA_CHECK(launch_blur(e->T, B, e->blurMaps, e->dBlurTiles, e->nBlurTiles, imgBase, batch, s)); }
   { StageTimer t(e, 4); ORBGPU_CUDA_CHECK(lat ? launch_describe_lat(e->T, B, e->descDiscMaps, e->descPatchMaps, imgBase, batch, s) : launch_describe(e->T, B, e->descDiscMaps, e->descPatchMaps, imgBase, batch, s)); }

@@ -2,15 +2,20 @@
 // (ORBextractor.cc:76-100, 466-473), computeOrbDescriptor (ORBextractor.cc:102-146) and the
 // tail of ORBextractor::operator() (ORBextractor.cc:1023-1037).
 //
-// One warp = one keypoint.
-//  * IC_Angle: 31 row reads of the staged disc of the UNBLURRED level (lane = column u, immediate offsets), integer moments
-//    m10 / m01 reduced by shuffles (exact, order-free), then cv::fastAtan2's float polynomial with
+// One HALF-warp = one keypoint (two keypoints per warp): the per-keypoint scalar work — level lookup, cv::fastAtan2, the
+// double-precision sincos, the output record — is issued once per warp instruction for two keypoints instead of one.
+//  * both neighbourhoods are staged in the half-warp's shared-memory slot by TWO TMA tensor copies per keypoint (the 31 x 31
+//    orientation disc from the level, the 37 x 37 patch from its blurred copy; pattern reach <= 18 px; box columns start on
+//    a 16-byte boundary, so rows are 48 / 64 bytes) on one mbarrier per warp — the 512 rotated sample positions are a scatter
+//    that would otherwise cost one 32-byte L2 sector per sample.
+//  * IC_Angle: lane = disc ROW (two rows per lane): a row is eight words re-aligned to u = -15, masked to the circle (per-row byte masks,
+//    L1-resident table) and reduced by two byte dot products per word — sum(u * I) with the constant weight words
+//    -15 .. 15 and sum(I) with ones (IDP.4A) — instead of one byte load and two integer operations per pixel; integer
+//    moments m10 / m01 reduced over the 16 lanes by shuffles (exact, order-free), then cv::fastAtan2's float polynomial with
 //    round-to-nearest mul/add/div intrinsics (the reference build never fuses into FMAs).
-//  * both neighbourhoods are staged in the warp's shared-memory slot by TWO TMA tensor copies per keypoint (the 31 x 31
-//    orientation disc from the level, the 37 x 37 patch from its blurred copy; pattern reach <= 18 px) — the 512 rotated
-//    sample positions are a scatter that would otherwise cost one 32-byte L2 sector per sample; then lane i builds
-//    descriptor byte i from 16 pattern points rotated by (cos, sin) of the angle.  cosf/sinf replicate glibc's double-precision sincosf algorithm (see sincos_glibc) so
-//    that cvRound(x*b + y*a) lands on the same pixel as on the host.
+//  * lane i of the half builds descriptor bytes i and i + 16 from 2 x 16 pattern points rotated by (cos, sin) of the angle.
+//    cosf/sinf replicate glibc's double-precision sincosf algorithm (see sincos_glibc) so that cvRound(x*b + y*a) lands on
+//    the same pixel as on the host.
 //  * The keypoint record (cv::KeyPoint layout) and the 32-byte descriptor row go straight to their
 //    final, level-major slot: start = sum of the lower levels' octree counts.
 #include <mutex>
@@ -29,9 +34,22 @@ __device__ const signed char d_pattern[1024] = {
 // consecutive 8-byte entries: entry [j][lane] = point 16*lane + j.  Filled once per device by k_init_pattern; 4 KB,
 // L1-resident for the descriptor loop.
 __device__ float2 d_patternT[512];
+// Byte masks of the orientation disc: word k of row i (v = i - 15) covers u = -15 + 4k .. -12 + 4k; a byte is 0xff where
+// |u| <= umax[|v|] (ORBextractor.cc:449-463).  1 KB, filled with the pattern table.
+__device__ __align__(16) unsigned d_discMask[31 * 8];
 __global__ void k_init_pattern() {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 512) d_patternT[(i & 15) * 32 + (i >> 4)] = make_float2((float)d_pattern[2 * i], (float)d_pattern[2 * i + 1]);
+  if (i < 31 * 8) {
+    const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    const int v = i / 8 - 15, k = i & 7, um = umax[v < 0 ? -v : v];
+    unsigned m = 0u;
+    for (int j = 0; j < 4; j++) {
+      const int u = -15 + 4 * k + j;
+      if (u >= -um && u <= um) m |= 0xffu << (8 * j);
+    }
+    d_discMask[i] = m;
+  }
 }
 
 // cv::fastAtan2(y, x) scalar path (called at ORBextractor.cc:99): degrees in [0, 360).
@@ -114,18 +132,36 @@ __device__ __forceinline__ void sincos_glibc(float y, float *sinp, float *cosp) 
 #define ORBGPU_DESCRIBE_WARPS 4
 #endif
 constexpr int kWarpsPerCta = ORBGPU_DESCRIBE_WARPS;
+constexpr int kKpPerWarp = 2;
 constexpr int kPatchR = 18;                    // |rotated pattern coordinate| <= round(13 * sqrt 2) = 18 < EDGE_THRESHOLD
 constexpr int kPatchRows = 2 * kPatchR + 1;    // 37
 // Both neighbourhoods of a keypoint arrive as TMA boxes (cp.async.bulk.tensor.3d on the level's [batch][rows][pitch] maps,
-// one per-warp mbarrier): the 31 x 31 orientation disc from the pyramid level and the 37 x 37 patch from the blurred level.
-// Box columns start on the 16-byte boundary at or before the first needed pixel, so the boxes are 48 and 64 bytes wide.
-constexpr int kDiscW = 48, kDiscRows = 2 * kHalfPatch + 1;        // 15 alignment bytes + 31 <= 48
-constexpr int kPatchW = 64;                                        // 15 alignment bytes + 37 <= 64
+// one mbarrier per warp): the 31 x 31 orientation disc from the pyramid level and the 37 x 37 patch from the blurred level.
+// Box columns start on the 16-byte boundary at or before the first needed pixel (48 / 64-byte rows; the disc's words are
+// re-aligned by funnel shifts).  ORBGPU_DESCRIBE_EXACT_BOX = 1 starts the boxes at the first needed column instead (32 / 48-byte
+// rows, no re-alignment): built and run once on the B200 (gpurun_out/r2n) — the extraction call returned an error with it and the
+// cause was not chased (GPU budget), so it stays off; the aligned form is the parity-tested one.
+#ifndef ORBGPU_DESCRIBE_EXACT_BOX
+#define ORBGPU_DESCRIBE_EXACT_BOX 0
+#endif
+#if ORBGPU_DESCRIBE_EXACT_BOX
+constexpr int kDiscW = 32, kPatchW = 48;
+#else
+constexpr int kDiscW = 48, kPatchW = 64;       // 15 alignment bytes + 31 <= 48, + 37 <= 64
+#endif
+constexpr int kDiscRows = 2 * kHalfPatch + 1;
 constexpr int kDiscBytes = kDiscW * kDiscRows, kPatchBytes = kPatchW * kPatchRows;
 constexpr int kDiscSlot = (kDiscBytes + 127) & ~127, kPatchSlot = (kPatchBytes + 127) & ~127;
-constexpr int kWarpSlot = kDiscSlot + kPatchSlot;
+constexpr int kKpSlot = kDiscSlot + kPatchSlot;
+constexpr int kWarpSlot = kKpPerWarp * kKpSlot;
 
-// blockIdx.x = chunk of kWarpsPerCta output slots (level-major keypoint index), blockIdx.y = image
+__device__ __forceinline__ int dp4a_us(unsigned data, unsigned weights, int acc) {     // sum of u8 x s8 products
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(data), "r"(weights), "r"(acc));
+  return d;
+}
+
+// blockIdx.x = chunk of 2 * kWarpsPerCta output slots (level-major keypoint index), blockIdx.y = image
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_describe(const __grid_constant__ TmaMaps pyrMaps, const __grid_constant__ TmaMaps blurMaps, const LevelTable *__restrict__ T,
            const int4 *__restrict__ selAll, const int *__restrict__ selCount, orbgpu_keypoint *__restrict__ kps,
@@ -135,9 +171,10 @@ k_describe(const __grid_constant__ TmaMaps pyrMaps, const __grid_constant__ TmaM
 
   const int img = imgBase + blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int slot = blockIdx.x * kWarpsPerCta + warp;                    // output row of this warp's keypoint
+  const int half = lane >> 4, l16 = lane & 15;
+  const int slot0 = (blockIdx.x * kWarpsPerCta + warp) * kKpPerWarp;    // output row of the warp's first keypoint
   // the image's output rows are level-major: lane l holds the end (exclusive) of level l's rows after a warp scan of the
-  // per-level octree counts; the keypoint's level is the number of levels that end at or before its slot
+  // per-level octree counts; a keypoint's level is the number of levels that end at or before its slot
   const int nlevels = T->nlevels;
   int levelEnd = lane < nlevels ? selCount[img * kMaxLevels + lane] : 0;
 #pragma unroll
@@ -146,54 +183,81 @@ k_describe(const __grid_constant__ TmaMaps pyrMaps, const __grid_constant__ TmaM
     if (lane >= o) levelEnd += v;
   }
   const int total = __shfl_sync(0xffffffffu, levelEnd, nlevels - 1);
-  const int level = min(__popc(__ballot_sync(0xffffffffu, lane < nlevels && slot >= levelEnd)), nlevels - 1);
-  const int start = level ? __shfl_sync(0xffffffffu, levelEnd, level - 1) : 0;
   const int kpCap = T->kpCap;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     kpCount[img] = min(total, kpCap);
     if (total > kpCap) atomicOr(status, kStatusKpOverflow);
   }
-  if (slot >= total || slot >= kpCap) return;
+  const int limit = min(total, kpCap);
+  if (slot0 >= limit) return;                                           // warp-uniform
+  const bool live = slot0 + half < limit;
+  const int slot = live ? slot0 + half : slot0;                         // an idle second half repeats the first keypoint and stores nothing
+  const int lvA = __popc(__ballot_sync(0xffffffffu, lane < nlevels && slot0 >= levelEnd));
+  const int lvB = __popc(__ballot_sync(0xffffffffu, lane < nlevels && slot0 + 1 >= levelEnd));
+  const int level = min(live && half ? lvB : lvA, nlevels - 1);
+  const int startSrc = __shfl_sync(0xffffffffu, levelEnd, max(level - 1, 0));
+  const int start = level ? startSrc : 0;
   const LevelGeom &G = T->lv[level];
   const int4 s = selAll[G.selOffset + (size_t)img * G.selCap + (slot - start)];   // x_level, y_level, response
 
   // ---- stage both neighbourhoods: two tensor copies per keypoint, no per-row address arithmetic, one memory latency
-  uint8_t *disc = smemRaw + ((128u - (smem_u32(smemRaw) & 127u)) & 127u) + warp * kWarpSlot;
+  uint8_t *disc = smemRaw + ((128u - (smem_u32(smemRaw) & 127u)) & 127u) + warp * kWarpSlot + half * kKpSlot;
   uint8_t *patch = disc + kDiscSlot;
   const int dx0 = s.x + kEdge - kHalfPatch, px0 = s.x + kEdge - kPatchR;      // padded columns of u = -15 / of the patch's first pixel
+#if ORBGPU_DESCRIBE_EXACT_BOX
+  const int dBox = dx0, pBox = px0, lead = 0;
+#else
+  const int dBox = dx0 & ~15, pBox = px0 & ~15, lead = px0 & 15;
+#endif
   if (lane == 0) {
     mbar_init(&sBar[warp], 1);
     mbar_fence_init();
-    mbar_expect_tx(&sBar[warp], kDiscBytes + kPatchBytes);
-    tma_load_3d(disc, &pyrMaps.m[level], dx0 & ~15, s.y + kEdge - kHalfPatch, img, &sBar[warp]);
-    tma_load_3d(patch, &blurMaps.m[level], px0 & ~15, s.y + kEdge - kPatchR, img, &sBar[warp]);
+    mbar_expect_tx(&sBar[warp], kKpPerWarp * (kDiscBytes + kPatchBytes));
   }
   __syncwarp();
-  static constexpr int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};   // ORBextractor.cc:449-463
-  const int u = lane - kHalfPatch;
-  const int au = abs(u);
-  mbar_wait(&sBar[warp], 0);
-  int ring[2 * kHalfPatch + 1];
-  {
-    const uint8_t *rp = disc + (dx0 & 15) + min(lane, 2 * kHalfPatch);     // lane = column u + 15 (lane 31 idle)
-#pragma unroll
-    for (int i = 0; i <= 2 * kHalfPatch; i++) {
-      const int v = i - kHalfPatch;
-      ring[i] = (lane < 31 && au <= kUmax[v < 0 ? -v : v]) ? (int)rp[i * kDiscW] : 0;
-    }
+  if (l16 == 0) {
+    tma_load_3d(disc, &pyrMaps.m[level], dBox, s.y + kEdge - kHalfPatch, img, &sBar[warp]);
+    tma_load_3d(patch, &blurMaps.m[level], pBox, s.y + kEdge - kPatchR, img, &sBar[warp]);
   }
-  const int lead = px0 & 15;
+  __syncwarp();
+  mbar_wait(&sBar[warp], 0);
 
-  // ---- IC_Angle
+  // ---- IC_Angle: rows l16 and l16 + 16 of the disc
   int m10 = 0, m01 = 0;
 #pragma unroll
-  for (int i = 0; i <= 2 * kHalfPatch; i++) {
-    m10 += ring[i];
-    m01 += (i - kHalfPatch) * ring[i];
-  }
-  m10 *= u;
+  for (int rr = 0; rr < 2; rr++) {
+    const int i = l16 + 16 * rr;
+    if (i < kDiscRows) {
+      unsigned D[8];
+#if ORBGPU_DESCRIBE_EXACT_BOX
+      const uint4 lo = *reinterpret_cast<const uint4 *>(disc + i * kDiscW), hi = *reinterpret_cast<const uint4 *>(disc + i * kDiscW + 16);
+      D[0] = lo.x; D[1] = lo.y; D[2] = lo.z; D[3] = lo.w; D[4] = hi.x; D[5] = hi.y; D[6] = hi.z; D[7] = hi.w;
+#else
+      const unsigned *rw = reinterpret_cast<const unsigned *>(disc + i * kDiscW) + ((dx0 & 15) >> 2);
+      const unsigned sh = 8u * (unsigned)(dx0 & 3);
+      unsigned w[9];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+      for (int k = 0; k < 9; k++) w[k] = rw[k];
+#pragma unroll
+      for (int k = 0; k < 8; k++) D[k] = __funnelshift_r(w[k], w[k + 1], sh);
+#endif
+      const uint4 mlo = __ldg(reinterpret_cast<const uint4 *>(d_discMask + 8 * i)), mhi = __ldg(reinterpret_cast<const uint4 *>(d_discMask + 8 * i + 4));
+      const unsigned mk[8] = {mlo.x, mlo.y, mlo.z, mlo.w, mhi.x, mhi.y, mhi.z, mhi.w};
+      // weight words: the column offsets u = -15 + 4k + j as signed bytes (u = 16 is outside every mask)
+      const unsigned wu[8] = {0xf4f3f2f1u, 0xf8f7f6f5u, 0xfcfbfaf9u, 0x00fffefdu, 0x04030201u, 0x08070605u, 0x0c0b0a09u, 0x000f0e0du};
+      int rowSum = 0, rowM = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const unsigned d = D[k] & mk[k];
+        rowM = dp4a_us(d, wu[k], rowM);
+        rowSum = (int)__dp4a(d, 0x01010101u, (unsigned)rowSum);
+      }
+      m10 += rowM;
+      m01 += (i - kHalfPatch) * rowSum;
+    }
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {                                      // within the half-warp
     m10 += __shfl_xor_sync(0xffffffffu, m10, o);
     m01 += __shfl_xor_sync(0xffffffffu, m01, o);
   }
@@ -208,23 +272,30 @@ k_describe(const __grid_constant__ TmaMaps pyrMaps, const __grid_constant__ TmaM
   const float kMagic = 12582912.0f;
   const uint8_t *pb = patch;
   const unsigned off0 = (unsigned)(kPatchR * kPatchW + lead + kPatchR) - 0x4B400000u * (unsigned)(kPatchW + 1);   // mod 2^32
-  const float2 *p = d_patternT + lane;         // point 16*lane + j sits at p[32 * j]
-  unsigned val = 0;
+  unsigned val[2];
 #pragma unroll
-  for (int bit = 0; bit < 8; bit++) {
-    int t[2];
+  for (int hb = 0; hb < 2; hb++) {
+    const float2 *p = d_patternT + l16 + 16 * hb;         // point 16 * byte + j sits at p[32 * j], byte = l16 + 16 * hb
+    unsigned v8 = 0;
 #pragma unroll
-    for (int e = 0; e < 2; e++) {
-      const float2 q = __ldg(&p[32 * (2 * bit + e)]);
-      const unsigned ry = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(q.x, b), __fmul_rn(q.y, a)), kMagic));
-      const unsigned rx = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(q.x, a), __fmul_rn(q.y, b)), kMagic));
-      t[e] = pb[ry * (unsigned)kPatchW + rx + off0];
+    for (int bit = 0; bit < 8; bit++) {
+      int t[2];
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const float2 q = __ldg(&p[32 * (2 * bit + e)]);
+        const unsigned ry = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(q.x, b), __fmul_rn(q.y, a)), kMagic));
+        const unsigned rx = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(q.x, a), __fmul_rn(q.y, b)), kMagic));
+        t[e] = pb[ry * (unsigned)kPatchW + rx + off0];
+      }
+      v8 |= (unsigned)(t[0] < t[1]) << bit;
     }
-    val |= (unsigned)(t[0] < t[1]) << bit;
+    val[hb] = v8;
   }
+  if (!live) return;
   const size_t row = (size_t)img * kpCap + slot;
-  desc[row * 32 + lane] = (uint8_t)val;
-  if (lane == 0) {
+  desc[row * 32 + l16] = (uint8_t)val[0];
+  desc[row * 32 + 16 + l16] = (uint8_t)val[1];
+  if (l16 == 0) {
     orbgpu_keypoint o;
     o.x = (float)s.x; o.y = (float)s.y;
     if (level != 0) { o.x = __fmul_rn(o.x, G.scale); o.y = __fmul_rn(o.y, G.scale); }
@@ -305,7 +376,7 @@ cudaError_t VNAME(describe_configure)() {
 
 cudaError_t VNAME(launch_describe)(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &pyrMaps, const TmaMaps &blurMaps, int imgBase,
                                    int batch, cudaStream_t s) {
-  dim3 grid((T.kpCap + kWarpsPerCta - 1) / kWarpsPerCta, batch);
+  dim3 grid((T.kpCap + kKpPerWarp * kWarpsPerCta - 1) / (kKpPerWarp * kWarpsPerCta), batch);
   k_describe<<<grid, kWarpsPerCta * 32, VNAME(describe_smem_bytes)(), s>>>(pyrMaps, blurMaps, B.dT, B.sel, B.selCount, B.kps, B.desc, B.kpCount,
                                                                           B.status, imgBase);
   count_launch();

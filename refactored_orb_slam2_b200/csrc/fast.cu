@@ -93,26 +93,45 @@ static_assert(ring_dy(0) == 3 && ring_dy(1) == 3 && ring_dy(2) == 2 && ring_dy(3
               ring_dy(7) == -3 && ring_dy(8) == -3 && ring_dy(9) == -3 && ring_dy(10) == -2 && ring_dy(11) == -1 && ring_dy(12) == 0 &&
               ring_dy(13) == 1 && ring_dy(14) == 2 && ring_dy(15) == 3, "cv::FAST 9/16 ring, y offsets");
 
-struct Raw { unsigned w0, w1, w2; };   // bytes x-4 .. x+7 of one row around a lane's four pixels x .. x+3
+// Bytes x-4 .. x+7 (x+11 in the shifted form) of one row around a lane's 4-byte group at padded column x
+struct Raw { unsigned w0, w1, w2, w3; };
 
+template <bool kShift>
 __device__ __forceinline__ Raw load_row(const uint8_t *p) {
   Raw r;
   r.w0 = __ldg(reinterpret_cast<const unsigned *>(p) - 1);
   r.w1 = __ldg(reinterpret_cast<const unsigned *>(p));
   r.w2 = __ldg(reinterpret_cast<const unsigned *>(p) + 1);
+  r.w3 = kShift ? __ldg(reinterpret_cast<const unsigned *>(p) + 2) : 0u;
   return r;
 }
-// the nine packed u16x2 pixel pairs (x+s, x+s+1), s = -3 .. 5, of one row: win[s + 3]
+// The nine packed u16x2 pixel pairs (x'+s, x'+s+1), s = -3 .. 5, of one row: win[s + 3].  x' = the lane's first pixel: byte
+// x of the row in the plain form, byte x + 2 in the shifted form (a strip of four 32-pixel cells starts two bytes off the
+// plane's 4-byte grid and would otherwise need a 33rd lane; it costs one more word per row and lane).  Pairs that straddle a
+// word take their zero bytes from a shifted copy made on the FMA pipe.
+template <bool kShift>
 __device__ __forceinline__ void unpack_row(const Raw &r, unsigned (&win)[9], const FmaConsts &K) {
-  win[0] = __byte_perm(r.w0, 0u, 0x4241u);
-  win[1] = __byte_perm(r.w0, 0u, 0x4342u);
-  win[2] = __byte_perm(top_byte_fma(r.w0, K), r.w1, 0x1410u);         // (w0.b3, w1.b0): the shifted word supplies the zero bytes
-  win[3] = __byte_perm(r.w1, 0u, 0x4140u);
-  win[4] = __byte_perm(r.w1, 0u, 0x4241u);
-  win[5] = __byte_perm(r.w1, 0u, 0x4342u);
-  win[6] = __byte_perm(top_byte_fma(r.w1, K), r.w2, 0x1410u);
-  win[7] = __byte_perm(r.w2, 0u, 0x4140u);
-  win[8] = __byte_perm(r.w2, 0u, 0x4241u);
+  if (!kShift) {
+    win[0] = __byte_perm(r.w0, 0u, 0x4241u);
+    win[1] = __byte_perm(r.w0, 0u, 0x4342u);
+    win[2] = __byte_perm(top_byte_fma(r.w0, K), r.w1, 0x1410u);         // (w0.b3, w1.b0): the shifted word supplies the zero bytes
+    win[3] = __byte_perm(r.w1, 0u, 0x4140u);
+    win[4] = __byte_perm(r.w1, 0u, 0x4241u);
+    win[5] = __byte_perm(r.w1, 0u, 0x4342u);
+    win[6] = __byte_perm(top_byte_fma(r.w1, K), r.w2, 0x1410u);
+    win[7] = __byte_perm(r.w2, 0u, 0x4140u);
+    win[8] = __byte_perm(r.w2, 0u, 0x4241u);
+  } else {
+    win[0] = __byte_perm(top_byte_fma(r.w0, K), r.w1, 0x1410u);         // bytes x-1, x
+    win[1] = __byte_perm(r.w1, 0u, 0x4140u);
+    win[2] = __byte_perm(r.w1, 0u, 0x4241u);
+    win[3] = __byte_perm(r.w1, 0u, 0x4342u);                            // the lane's own first pair: bytes x+2, x+3
+    win[4] = __byte_perm(top_byte_fma(r.w1, K), r.w2, 0x1410u);
+    win[5] = __byte_perm(r.w2, 0u, 0x4140u);
+    win[6] = __byte_perm(r.w2, 0u, 0x4241u);
+    win[7] = __byte_perm(r.w2, 0u, 0x4342u);
+    win[8] = __byte_perm(top_byte_fma(r.w2, K), r.w3, 0x1410u);         // bytes x+7, x+8
+  }
 }
 
 // Pulls the line(s) of a later row towards L1 without tying up a register: the three LDGs of that row then hit.  Rows past
@@ -154,11 +173,106 @@ __device__ __forceinline__ void nms_row(const NmsState &st, unsigned h3P, unsign
   }
 }
 
+#if ORBGPU_FAST_DEFER
+// Deferred form: the row's decision leaves the loop as ONE word per lane — the lane's four scores as bytes (score <= 255 -
+// minTh), zero where the pixel does not survive — stored without a branch to the warp's score rows in shared memory; the
+// survivors (about 2 % of the pixels, yet 9 of 10 warp rows have one) are collected after the march by a sweep that only
+// visits the non-zero words, instead of a divergent append behind a branch that is taken in nearly every step.
+__device__ __forceinline__ unsigned nms_row_scores(const NmsState &st, unsigned h3P, unsigned h3Q, const LaneMasks &M, const FmaConsts &K) {
+  const unsigned nbP = mx3(st.h3ppP, st.sideP, h3P), nbQ = mx3(st.h3ppQ, st.sideQ, h3Q);
+  const unsigned kP = ~__vadd2(st.sP, not_fma(nbP, K)) & M.vP, kQ = ~__vadd2(st.sQ, not_fma(nbQ, K)) & M.vQ;   // bit 15 / 31 per surviving pixel
+  unsigned keep;                                                        // sign of bytes 1, 3, 5, 7 replicated: 0xff per surviving pixel
+  asm("prmt.b32 %0, %1, %2, 0xfdb9;" : "=r"(keep) : "r"(kP), "r"(kQ));     // (__byte_perm drops the selector's replicate bits)
+  return __byte_perm(st.sP, st.sQ, 0x6420u) & keep;                     // the four scores' low bytes
+}
+#endif
+
+// The march of one warp down its strip: rows Y0 - 3 .. Y1 + 2 through the rolling register window, scores, NMS, survivors to the stage list
+// (deferred form: to the lane's column of the score rows, row y at rowsBuf[(y + 1) * 32]; row 0 takes the first step's empty decision).
+template <bool kShift>
+__device__ __forceinline__ void march_strip(const uint8_t *rowPtr, int pitch, int pfOff, int TH, const LaneMasks &M, int x0, unsigned k1,
+                                            unsigned *stage, int *stageCount, int stageCap, unsigned *rowsBuf, const FmaConsts &K) {
+  unsigned win[7][9];                                // rolling window: row r of the strip's source rows lives in slot r % 7
+  NmsState st = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+  const int nRows = TH + 6;                          // source rows Y0 - 3 .. Y1 + 2
+#pragma unroll
+  for (int i = 0; i < kPrefetchRows; i++) prefetch_l1(rowPtr + (kAhead + i) * pitch + pfOff);
+  // raw rows in flight: row r is unpacked from raw[r % 7] while row r + kAhead is being loaded into raw[(r + kAhead) % 7] (a
+  // ring indexed like the window, so no register is ever copied from a load's destination before its data is needed)
+  Raw raw[7];
+#pragma unroll
+  for (int i = 0; i < kAhead; i++) raw[i] = load_row<kShift>(rowPtr + i * pitch);
+  for (int r0 = 0; r0 < nRows; r0 += 7) {
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+      const int r = r0 + k;
+      if (r < nRows) {
+        raw[(k + kAhead) % 7] = load_row<kShift>(rowPtr + kAhead * pitch);       // row r + kAhead (always inside the padded plane)
+        prefetch_l1(rowPtr + (kAhead + kPrefetchRows) * pitch + pfOff);          // and later rows on their way from HBM / L2 into L1
+        rowPtr += pitch;
+        unpack_row<kShift>(raw[k], win[k], K);
+        if (r >= 6) {
+          // pixel row y = r - 6: its ring rows y-3 .. y+3 are the source rows r-6 .. r = slots (k + 1 + i) % 7
+          unsigned dP[16], dQ[16];
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            const int slot = (k + 4 + ring_dy(i)) % 7;
+            dP[i] = win[slot][ring_dx(i) + 3];
+            dQ[i] = win[slot][ring_dx(i) + 5];
+          }
+          const unsigned sP = score_of_ring(dP, win[(k + 4) % 7][3], k1, K);
+          const unsigned sQ = score_of_ring(dQ, win[(k + 4) % 7][5], k1, K);
+          // horizontal neighbours: (x-1, x) / (x+1, x+2) / (x+3, x+4) as packed pairs, cell borders masked out
+          const unsigned prevQ = __shfl_up_sync(0xffffffffu, sQ, 1), nextP = __shfl_down_sync(0xffffffffu, sP, 1);
+          const unsigned mid = __byte_perm(sP, sQ, 0x5432u);
+          const unsigned LP = __byte_perm(prevQ, sP, 0x5432u) & M.mLP, RP = mid & M.mRP;
+          const unsigned LQ = mid & M.mLQ, RQ = __byte_perm(sQ, nextP, 0x5432u) & M.mRQ;
+          const unsigned h3P = mx3(LP, sP, RP), h3Q = mx3(LQ, sQ, RQ);
+#if ORBGPU_FAST_DEFER
+          rowsBuf[(r - 6) * 32] = nms_row_scores(st, h3P, h3Q, M, K);              // row y - 1 (all zero for y = 0: the spare row)
+#else
+          nms_row(st, h3P, h3Q, M, x0, r - 7, stage, stageCount, stageCap, K);     // row y - 1 (nothing survives for y = 0)
+#endif
+          st.h3ppP = st.h3P; st.h3ppQ = st.h3Q; st.h3P = h3P; st.h3Q = h3Q;
+          st.sP = sP; st.sQ = sQ; st.sideP = mx2(LP, RP); st.sideQ = mx2(LQ, RQ);
+        }
+      }
+    }
+  }
+#if ORBGPU_FAST_DEFER
+  rowsBuf[TH * 32] = nms_row_scores(st, 0u, 0u, M, K);                             // last row: nothing below it
+  // sweep: a bit per non-zero word of the lane's column, then only those words are opened
+  for (int h = 0; h < TH; h += 32) {
+    const int n = min(32, TH - h);
+    unsigned m = 0u;
+    for (int y = 0; y < n; y++) m |= (rowsBuf[(h + y + 1) * 32] != 0u ? 1u : 0u) << y;
+    while (m != 0u) {
+      const int y = h + __ffs((int)m) - 1;
+      m &= m - 1u;
+      const unsigned v = rowsBuf[(y + 1) * 32];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const unsigned sc = (v >> (8 * j)) & 0xffu;
+        if (sc != 0u) {
+          const int at = atom_add_shared(stageCount, 1);
+          if (at < stageCap) stage[at] = (unsigned)(x0 + j) | ((unsigned)y << 7) | (sc << 13);
+        }
+      }
+    }
+  }
+#else
+  nms_row(st, 0u, 0u, M, x0, TH - 1, stage, stageCount, stageCap, K);              // last row: nothing below it
+#endif
+}
+
+// kShift: the launch's strips all run in the shifted form (fast_strip_shifted; the host keeps the two kinds in separate
+// launches so that each kernel carries one copy of the unrolled march — both copies in one kernel thrash the instruction cache)
+template <bool kShift>
 __global__ void __launch_bounds__(kThreads, ORBGPU_FAST_CTAS_PER_SM)
 k_fast_strips(const LevelTable *__restrict__ T, const int4 *__restrict__ strips, int nstrips, int totalItems, int imgBase,
               const uint8_t *__restrict__ pyr, Cand *__restrict__ cand, int *__restrict__ candCount, unsigned *__restrict__ status,
-              int stageCap, const FmaConsts K) {
-  extern __shared__ unsigned sStageAll[];            // [kWarps][stageCap]
+              int stageCap, int rowsCap, const FmaConsts K) {
+  extern __shared__ unsigned sStageAll[];            // [kWarps][stageCap], then [kWarps][rowsCap][32] score rows (deferred form)
   __shared__ int sCount[kWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * kWarps + warp;
@@ -172,10 +286,13 @@ k_fast_strips(const LevelTable *__restrict__ T, const int4 *__restrict__ strips,
   const int X0 = kEdge + strip.z * G.wCell, Y0 = kEdge + strip.y * G.hCell;
   const int X1 = min(kEdge + (strip.z + strip.w) * G.wCell, G.w - kEdge), Y1 = min(Y0 + G.hCell, G.h - kEdge);
   const int TW = X1 - X0, TH = Y1 - Y0;
-  const int gx0 = (X0 + kEdge) & ~3;                 // padded column of lane 0's first pixel (4-byte grid)
-  const int offL = (X0 + kEdge) - gx0;               // strip x = 4 * lane + j - offL
+  const int gx0 = (X0 + kEdge) & ~3;                 // padded column of lane 0's 4-byte group
+  // strip x = 4 * lane + j - offL.  A strip that would need a 33rd lane (four 32-pixel cells start two bytes off the 4-byte
+  // grid) runs in the shifted form: every lane's pixels start at byte 2 of its group (one more word per row and lane)
+  const int offL = (X0 + kEdge) - gx0 - (kShift ? 2 : 0);
   const int wCell = G.wCell;
   unsigned *stage = sStageAll + warp * stageCap;
+  unsigned *rowsBuf = sStageAll + kWarps * stageCap + warp * rowsCap * 32 + lane;
   int *stageCount = &sCount[warp];
   if (lane == 0) *stageCount = 0;
   __syncwarp();
@@ -200,53 +317,10 @@ k_fast_strips(const LevelTable *__restrict__ T, const int4 *__restrict__ strips,
   const int iniS = iniTh - minTh;                    // score > iniS  <=>  margin > iniTh
   const int pitch = G.pitch;
   const uint8_t *rowPtr = pyr + G.pyrOffset + (size_t)img * G.planeBytes + (size_t)(Y0 - 3 + kEdge) * pitch + gx0 + 4 * lane;
-  // prefetch addresses cover the whole 136-byte span the warp reads per row (lane 0 its left word, lane 31 its right word)
-  const int pfOff = lane == 31 ? 4 : -4;
+  // prefetch addresses cover the whole 136 / 140-byte span the warp reads per row (lane 0 its left word, lane 31 its right word)
+  const int pfOff = lane == 31 ? (kShift ? 8 : 4) : -4;
 
-  unsigned win[7][9];                                // rolling window: row r of the strip's source rows lives in slot r % 7
-  NmsState st = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-  const int nRows = TH + 6;                          // source rows Y0 - 3 .. Y1 + 2
-#pragma unroll
-  for (int i = 0; i < kPrefetchRows; i++) prefetch_l1(rowPtr + (kAhead + i) * pitch + pfOff);
-  // raw rows in flight: row r is unpacked from raw[r % 7] while row r + kAhead is being loaded into raw[(r + kAhead) % 7] (a
-  // ring indexed like the window, so no register is ever copied from a load's destination before its data is needed)
-  Raw raw[7];
-#pragma unroll
-  for (int i = 0; i < kAhead; i++) raw[i] = load_row(rowPtr + i * pitch);
-  for (int r0 = 0; r0 < nRows; r0 += 7) {
-#pragma unroll
-    for (int k = 0; k < 7; k++) {
-      const int r = r0 + k;
-      if (r < nRows) {
-        raw[(k + kAhead) % 7] = load_row(rowPtr + kAhead * pitch);       // row r + kAhead (always inside the padded plane)
-        prefetch_l1(rowPtr + (kAhead + kPrefetchRows) * pitch + pfOff);          // and later rows on their way from HBM / L2 into L1
-        rowPtr += pitch;
-        unpack_row(raw[k], win[k], K);
-        if (r >= 6) {
-          // pixel row y = r - 6: its ring rows y-3 .. y+3 are the source rows r-6 .. r = slots (k + 1 + i) % 7
-          unsigned dP[16], dQ[16];
-#pragma unroll
-          for (int i = 0; i < 16; i++) {
-            const int slot = (k + 4 + ring_dy(i)) % 7;
-            dP[i] = win[slot][ring_dx(i) + 3];
-            dQ[i] = win[slot][ring_dx(i) + 5];
-          }
-          const unsigned sP = score_of_ring(dP, win[(k + 4) % 7][3], k1, K);
-          const unsigned sQ = score_of_ring(dQ, win[(k + 4) % 7][5], k1, K);
-          // horizontal neighbours: (x-1, x) / (x+1, x+2) / (x+3, x+4) as packed pairs, cell borders masked out
-          const unsigned prevQ = __shfl_up_sync(0xffffffffu, sQ, 1), nextP = __shfl_down_sync(0xffffffffu, sP, 1);
-          const unsigned mid = __byte_perm(sP, sQ, 0x5432u);
-          const unsigned LP = __byte_perm(prevQ, sP, 0x5432u) & M.mLP, RP = mid & M.mRP;
-          const unsigned LQ = mid & M.mLQ, RQ = __byte_perm(sQ, nextP, 0x5432u) & M.mRQ;
-          const unsigned h3P = mx3(LP, sP, RP), h3Q = mx3(LQ, sQ, RQ);
-          nms_row(st, h3P, h3Q, M, x0, r - 7, stage, stageCount, stageCap, K);     // row y - 1 (nothing survives for y = 0)
-          st.h3ppP = st.h3P; st.h3ppQ = st.h3Q; st.h3P = h3P; st.h3Q = h3Q;
-          st.sP = sP; st.sQ = sQ; st.sideP = mx2(LP, RP); st.sideQ = mx2(LQ, RQ);
-        }
-      }
-    }
-  }
-  nms_row(st, 0u, 0u, M, x0, TH - 1, stage, stageCount, stageCap, K);              // last row: nothing below it
+  march_strip<kShift>(rowPtr, pitch, pfOff, TH, M, x0, k1, stage, stageCount, stageCap, rowsBuf, K);
 
   // ---- emit: cells with no survivor at iniTh fall back to minTh (ORBextractor.cc:776-780)
   __syncwarp();
@@ -288,9 +362,22 @@ k_fast_strips(const LevelTable *__restrict__ T, const int4 *__restrict__ strips,
 
 }  // namespace
 
-// Cells per strip of a level: as many (up to 4) as fit 128 pixels including the up to 3 pixels the strip's first
-// 4-pixel group starts before it.
-int fast_cells_per_strip(int wCell) { return wCell <= 31 ? 4 : wCell <= 41 ? 3 : wCell <= 62 ? 2 : 1; }
+// Cells per strip of a level: as many (up to 4) as fit 128 pixels.  A strip starts 0 .. 3 bytes off the plane's 4-byte grid
+// (padded column 38 + j * wCell); the shifted mode removes two of them, so at most one lane-pixel is lost: none when wCell
+// is even (then the offset is even), one when it is odd.
+bool fast_strip_shifted(const LevelGeom &G, int firstCell, int cells) {
+  const int X0 = kEdge + firstCell * G.wCell, X1 = min(kEdge + (firstCell + cells) * G.wCell, G.w - kEdge);
+  const int off = (X0 + kEdge) & 3;
+  return ORBGPU_FAST_SHIFT && off >= 2 && X1 - X0 + off > 128;
+}
+
+int fast_cells_per_strip(int wCell) {
+#if ORBGPU_FAST_SHIFT
+  return min(4, max(1, (128 - (wCell & 1)) / wCell));
+#else
+  return wCell <= 31 ? 4 : wCell <= 41 ? 3 : wCell <= 62 ? 2 : 1;
+#endif
+}
 
 // Stage-list entries per warp: NMS survivors are strict 8-neighbour maxima inside one cell rectangle, at most
 // ceil(cw / 2) * ceil(ch / 2) per cell.
@@ -302,21 +389,36 @@ FastConfig fast_make_config(const LevelTable &T) {
     cap = max(cap, fast_cells_per_strip(G.wCell) * ((G.wCell + 1) / 2) * ((G.hCell + 1) / 2));
   }
   c.stageCap = cap;
-  c.smemBytes = kWarps * cap * (int)sizeof(unsigned);
+  int rows = 0;
+#if ORBGPU_FAST_DEFER
+  for (int l = 0; l < T.nlevels; l++) rows = max(rows, T.lv[l].hCell + 1);      // score rows: one per detection row + the spare row 0
+#endif
+  c.rowsCap = rows;
+  c.smemBytes = kWarps * (cap + rows * 32) * (int)sizeof(unsigned);
   return c;
 }
 
 cudaError_t fast_configure(int smemBytes) {
-  return cudaFuncSetAttribute(k_fast_strips, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
+  const cudaError_t e = cudaFuncSetAttribute(k_fast_strips<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
+  return e != cudaSuccess ? e : cudaFuncSetAttribute(k_fast_strips<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
 }
 
-cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const int4 *strips, int nstrips, const FastConfig &c,
+// strips[0 .. nPlain) run in the plain form, strips[nPlain .. nPlain + nShift) in the shifted form (fast_strip_shifted)
+cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const int4 *strips, int nPlain, int nShift, const FastConfig &c,
                         int imgBase, int batch, cudaStream_t s) {
-  const int total = nstrips * batch;
-  const int grid = (total + kWarps - 1) / kWarps;
-  k_fast_strips<<<grid, kThreads, c.smemBytes, s>>>(B.dT, strips, nstrips, total, imgBase, B.pyr, B.cand, B.candCount, B.status, c.stageCap,
-                                                     FmaConsts{0xffffffffu, 256u});
-  count_launch();
+  const FmaConsts K{0xffffffffu, 256u};
+  if (nPlain > 0) {
+    const int total = nPlain * batch;
+    k_fast_strips<false><<<(total + kWarps - 1) / kWarps, kThreads, c.smemBytes, s>>>(B.dT, strips, nPlain, total, imgBase, B.pyr, B.cand, B.candCount,
+                                                                                        B.status, c.stageCap, c.rowsCap, K);
+    count_launch();
+  }
+  if (nShift > 0) {
+    const int total = nShift * batch;
+    k_fast_strips<true><<<(total + kWarps - 1) / kWarps, kThreads, c.smemBytes, s>>>(B.dT, strips + nPlain, nShift, total, imgBase, B.pyr, B.cand, B.candCount,
+                                                                                       B.status, c.stageCap, c.rowsCap, K);
+    count_launch();
+  }
   return cudaGetLastError();
 }
 

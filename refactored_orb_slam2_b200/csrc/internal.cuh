@@ -126,13 +126,20 @@ void blur_make_tiles(const LevelTable &T, std::vector<int4> &tiles);
 #ifndef ORBGPU_FAST_PREFETCH
 #define ORBGPU_FAST_PREFETCH 4       // rows of L1 prefetch ahead of the register loads
 #endif
+#ifndef ORBGPU_FAST_SHIFT
+#define ORBGPU_FAST_SHIFT 1          // strips of four 32-pixel cells (2 bytes off the 4-byte grid) run shifted instead of as three cells
+#endif
+#ifndef ORBGPU_FAST_DEFER
+#define ORBGPU_FAST_DEFER 1          // NMS survivors leave the row loop as one score word per lane and row; collected after the march
+#endif
 #ifndef ORBGPU_FAST_AHEAD
 #define ORBGPU_FAST_AHEAD 1
 #endif
-struct FastConfig { int stageCap, smemBytes; };
+struct FastConfig { int stageCap, rowsCap, smemBytes; };
 int fast_cells_per_strip(int wCell);
 FastConfig fast_make_config(const LevelTable &T);
-cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const int4 *strips, int nstrips, const FastConfig &c,
+bool fast_strip_shifted(const LevelGeom &G, int firstCell, int cells);
+cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const int4 *strips, int nPlain, int nShift, const FastConfig &c,
                         int imgBase, int batch, cudaStream_t s);
 cudaError_t launch_octree(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, int smemBytes,
                           cudaStream_t s);

@@ -158,19 +158,30 @@ k_stereo_match(const LevelTable *__restrict__ T, StereoArgs A, int rows, int row
         off[t] = dy * G.pitch + dx;
         lv[t] = i < 121 ? (int)PL[off[t]] - centreL : 0;
       }
-      int best = 0x7fffffff, bestInc = 0;
-      float dist[11];
+      // per-lane partial SADs of the 11 shifts: |lv - (R - centreR)| = |(lv + centreR) - R| as one add + one absolute-difference-
+      // accumulate per pixel; the warp sums are exact integers <= 121 * 510 < 2^16, so two shifts share one 32-bit warp reduction
+      unsigned part[11];
 #pragma unroll
       for (int inc = -L; inc <= L; inc++) {
         const int centreR = PR[inc];
-        int sad = 0;
+        unsigned sad = 0;
 #pragma unroll
         for (int t = 0; t < 4; t++)
-          if (lane + 32 * t < 121) sad += abs(lv[t] - ((int)PR[off[t] + inc] - centreR));
+          if (lane + 32 * t < 121) sad = __sad(lv[t] + centreR, (int)PR[off[t] + inc], sad);
+        part[inc + L] = sad;
+      }
+      int best = 0x7fffffff, bestInc = 0;
+      float dist[11];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sad += __shfl_xor_sync(0xffffffffu, sad, o);
-        dist[inc + L] = (float)sad;
-        if (sad < best) { best = sad; bestInc = inc; }
+      for (int k = 0; k < 6; k++) {
+        const unsigned both = __reduce_add_sync(0xffffffffu, part[2 * k] | (k < 5 ? part[2 * k + 1] << 16 : 0u));
+        const int s0 = (int)(both & 0xffffu), s1 = (int)(both >> 16);
+        dist[2 * k] = (float)s0;
+        if (s0 < best) { best = s0; bestInc = 2 * k - L; }
+        if (k < 5) {
+          dist[2 * k + 1] = (float)s1;
+          if (s1 < best) { best = s1; bestInc = 2 * k + 1 - L; }
+        }
       }
       if (!(bestInc == -L || bestInc == L)) {
         float d1 = 0.f, d2 = 0.f, d3 = 0.f;

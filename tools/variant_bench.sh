@@ -6,7 +6,7 @@ run() {
   python bench.py --steps 10 --warmup 3 --no-hamming --no-cpu-baseline --no-latency --no-copy-probe 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
-print('$1', round(d['value']), 'fps', round(d['ms_per_step'],3), 'ms', {k:round(v,3) for k,v in d['stage_ms'].items()})"
+print('$1', round(d['value']), 'fps', round(d['ms_per_step'],3), 'ms', 'e2e', round(d['e2e']['value']), {k:round(v,3) for k,v in d['stage_ms'].items()})"
 }
 run default | tee "$out"
 for f in $(ls gpurun_variants/lib_*.so 2>/dev/null); do ORBGPU_LIB=$PWD/$f run "$(basename $f)" | tee -a "$out"; done

@@ -404,7 +404,7 @@ def run_own(args, rank, local_rank, world):
     same_api = bool(np.array_equal(nk, counts_dev))
     for i in range(0, nimg, max(1, nimg // 16)):
         same_api = same_api and np.array_equal(k_host[i, :nk[i]], kps_dev[i, :nk[i]]) and np.array_equal(out_d.numpy()[i, :nk[i]], desc_dev[i, :nk[i]])
-    depth = max(2, env_int("BENCH_PIPELINE_DEPTH", 2))
+    depth = max(2, env_int("BENCH_PIPELINE_DEPTH", 3))      # measured on one B200 (profiles/r2_e2e_knobs.txt): 2 -> 90.6 k, 3 -> 94.0 k frames/s
     dt, api = dt_sync, "orbgpu_extract_batch%s, pinned host buffers" % (" + orbgpu_stereo_match" if stereo else "")
     last_matched = None
     if stereo:

@@ -80,7 +80,8 @@ k_blur(const __grid_constant__ TmaMaps maps, const LevelTable *__restrict__ T, c
     for (int p = 0; p < 4; p++) P[k][p] = 0u;
 
   static_assert(kBoxH % 6 == 0, "row loop is unrolled by the pair-history depth");
-  for (int r0 = 0; r0 < kBoxH; r0 += 6) {
+  const int rEnd = min(kBoxH, (rowsOut + 6 + 5) / 6 * 6);     // a level's last tile row stops after its own rows (+ the 6 rows of history)
+  for (int r0 = 0; r0 < rEnd; r0 += 6) {
 #pragma unroll
     for (int rr = 0; rr < 6; rr++) {
       const int r = r0 + rr;

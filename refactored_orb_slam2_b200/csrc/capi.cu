@@ -86,7 +86,7 @@ struct orbgpu_extractor {
   unsigned *dStatus = nullptr;
   int kpCap = 0;
   // stereo results (owned by the LEFT handle)
-  float *dURight = nullptr, *dDepth = nullptr; int *dBestSad = nullptr, *dRowStart = nullptr, *dSorted = nullptr;
+  float *dURight = nullptr, *dDepth = nullptr; int *dBestSad = nullptr, *dRowStart = nullptr; int4 *dSorted = nullptr;
   cudaEvent_t evDone = nullptr;
   // the blur of a batch only needs its pyramid: it runs on a side stream next to FAST + octree and joins before describe
   cudaStream_t side = nullptr;
@@ -894,7 +894,7 @@ int orbgpu_stereo_match_device(orbgpu_extractor *L, orbgpu_extractor *R, int fir
     ORBGPU_CUDA_CHECK(cudaMalloc(&L->dURight, n * sizeof(float)));
     ORBGPU_CUDA_CHECK(cudaMalloc(&L->dDepth, n * sizeof(float)));
     ORBGPU_CUDA_CHECK(cudaMalloc(&L->dBestSad, n * sizeof(int)));
-    ORBGPU_CUDA_CHECK(cudaMalloc(&L->dSorted, n * sizeof(int)));
+    ORBGPU_CUDA_CHECK(cudaMalloc(&L->dSorted, n * sizeof(int4)));
     ORBGPU_CUDA_CHECK(cudaMalloc(&L->dRowStart, (size_t)L->p.max_batch * (L->p.max_height + 2) * sizeof(int)));
     ORBGPU_CUDA_CHECK(stereo_configure(L->p.max_height + 1));
     ORBGPU_CUDA_CHECK(stereo_configure_lat(L->p.max_height + 1));
@@ -907,7 +907,7 @@ int orbgpu_stereo_match_device(orbgpu_extractor *L, orbgpu_extractor *R, int fir
   A.pyrL = L->dPyr; A.pyrR = R->dPyr; A.kpsL = L->dKps; A.kpsR = R->dKps; A.descL = L->dDesc; A.descR = R->dDesc;
   A.cntL = L->dKpCount; A.cntR = R->dKpCount; A.kpCapL = L->kpCap; A.kpCapR = R->kpCap;
   A.firstL = first_left; A.firstR = first_right; A.pairs = pairs; A.mbf = mbf; A.mb = mb;
-  A.uRight = L->dURight; A.depth = L->dDepth; A.bestSad = L->dBestSad; A.rowStart = L->dRowStart; A.sorted = L->dSorted;
+  A.uRight = L->dURight; A.depth = L->dDepth; A.bestSad = L->dBestSad; A.rowStart = L->dRowStart; A.recs = L->dSorted;
   { StageTimer t(L, 5); ORBGPU_CUDA_CHECK(pairs <= kLatencyBatch / 2 ? launch_stereo_lat(L->T, L->dT, A, L->kpCap, L->stream) : launch_stereo(L->T, L->dT, A, L->kpCap, L->stream)); }
   if (R != L) {   // the right handle must not overwrite its buffers before the match has read them
     ORBGPU_CUDA_CHECK(cudaEventRecord(L->evDone, L->stream));

@@ -137,18 +137,10 @@ constexpr int kPatchR = 18;                    // |rotated pattern coordinate| <
 constexpr int kPatchRows = 2 * kPatchR + 1;    // 37
 // Both neighbourhoods of a keypoint arrive as TMA boxes (cp.async.bulk.tensor.3d on the level's [batch][rows][pitch] maps,
 // one mbarrier per warp): the 31 x 31 orientation disc from the pyramid level and the 37 x 37 patch from the blurred level.
-// Box columns start on the 16-byte boundary at or before the first needed pixel (48 / 64-byte rows; the disc's words are
-// re-aligned by funnel shifts).  ORBGPU_DESCRIBE_EXACT_BOX = 1 starts the boxes at the first needed column instead (32 / 48-byte
-// rows, no re-alignment): built and run once on the B200 (gpurun_out/r2n) — the extraction call returned an error with it and the
-// cause was not chased (GPU budget), so it stays off; the aligned form is the parity-tested one.
-#ifndef ORBGPU_DESCRIBE_EXACT_BOX
-#define ORBGPU_DESCRIBE_EXACT_BOX 0
-#endif
-#if ORBGPU_DESCRIBE_EXACT_BOX
-constexpr int kDiscW = 32, kPatchW = 48;
-#else
+// Box columns start on the 16-byte boundary at or before the first needed pixel — a tensor copy's start address must be
+// 16-byte aligned, which for these u8 planes means the innermost coordinate (boxes that started at the exact column failed on
+// the B200, gpurun_out/r2n) — so the rows are 48 / 64 bytes and the disc's words are re-aligned by funnel shifts.
 constexpr int kDiscW = 48, kPatchW = 64;       // 15 alignment bytes + 31 <= 48, + 37 <= 64
-#endif
 constexpr int kDiscRows = 2 * kHalfPatch + 1;
 constexpr int kDiscBytes = kDiscW * kDiscRows, kPatchBytes = kPatchW * kPatchRows;
 constexpr int kDiscSlot = (kDiscBytes + 127) & ~127, kPatchSlot = (kPatchBytes + 127) & ~127;
@@ -204,11 +196,7 @@ k_describe(const __grid_constant__ TmaMaps pyrMaps, const __grid_constant__ TmaM
   uint8_t *disc = smemRaw + ((128u - (smem_u32(smemRaw) & 127u)) & 127u) + warp * kWarpSlot + half * kKpSlot;
   uint8_t *patch = disc + kDiscSlot;
   const int dx0 = s.x + kEdge - kHalfPatch, px0 = s.x + kEdge - kPatchR;      // padded columns of u = -15 / of the patch's first pixel
-#if ORBGPU_DESCRIBE_EXACT_BOX
-  const int dBox = dx0, pBox = px0, lead = 0;
-#else
   const int dBox = dx0 & ~15, pBox = px0 & ~15, lead = px0 & 15;
-#endif
   if (lane == 0) {
     mbar_init(&sBar[warp], 1);
     mbar_fence_init();
@@ -229,10 +217,6 @@ k_describe(const __grid_constant__ TmaMaps pyrMaps, const __grid_constant__ TmaM
     const int i = l16 + 16 * rr;
     if (i < kDiscRows) {
       unsigned D[8];
-#if ORBGPU_DESCRIBE_EXACT_BOX
-      const uint4 lo = *reinterpret_cast<const uint4 *>(disc + i * kDiscW), hi = *reinterpret_cast<const uint4 *>(disc + i * kDiscW + 16);
-      D[0] = lo.x; D[1] = lo.y; D[2] = lo.z; D[3] = lo.w; D[4] = hi.x; D[5] = hi.y; D[6] = hi.z; D[7] = hi.w;
-#else
       const unsigned *rw = reinterpret_cast<const unsigned *>(disc + i * kDiscW) + ((dx0 & 15) >> 2);
       const unsigned sh = 8u * (unsigned)(dx0 & 3);
       unsigned w[9];
@@ -240,7 +224,6 @@ k_describe(const __grid_constant__ TmaMaps pyrMaps, const __grid_constant__ TmaM
       for (int k = 0; k < 9; k++) w[k] = rw[k];
 #pragma unroll
       for (int k = 0; k < 8; k++) D[k] = __funnelshift_r(w[k], w[k + 1], sh);
-#endif
       const uint4 mlo = __ldg(reinterpret_cast<const uint4 *>(d_discMask + 8 * i)), mhi = __ldg(reinterpret_cast<const uint4 *>(d_discMask + 8 * i + 4));
       const unsigned mk[8] = {mlo.x, mlo.y, mlo.z, mlo.w, mhi.x, mhi.y, mhi.z, mhi.w};
       // weight words: the column offsets u = -15 + 4k + j as signed bytes (u = 16 is outside every mask)

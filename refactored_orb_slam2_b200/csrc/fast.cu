@@ -151,6 +151,7 @@ __device__ __forceinline__ int atom_add_shared(int *p, int v) {   // plain ATOMS
 struct NmsState { unsigned sP, sQ, sideP, sideQ, h3P, h3Q, h3ppP, h3ppQ; };
 struct LaneMasks { unsigned mLP, mRP, mLQ, mRQ, vP, vQ; };
 
+#if !ORBGPU_FAST_DEFER
 // Decides row `yPrev` (scores in st.s*) now that the row below it is known (h3 of that row in h3P / h3Q; pass 0 below
 // the strip), and appends the survivors to the warp's stage list as  x | y << 7 | score << 13.  About 2 % of the pixels
 // survive, so the append is a short loop over the lane's set bits behind one rarely taken branch.
@@ -172,6 +173,7 @@ __device__ __forceinline__ void nms_row(const NmsState &st, unsigned h3P, unsign
     } while (bits != 0u);
   }
 }
+#endif
 
 #if ORBGPU_FAST_DEFER
 // Deferred form: the row's decision leaves the loop as ONE word per lane — the lane's four scores as bytes (score <= 255 -

@@ -174,7 +174,7 @@ struct StereoArgs {
   float *uRight, *depth;    // [pairs][kpCapL] (indexed from 0, i.e. relative to firstL)
   int *bestSad;             // [pairs][kpCapL]
   int *rowStart;            // [pairs][rows + 1]: right keypoints bucketed by image row
-  int *sorted;              // [pairs][kpCapR]
+  int4 *recs;               // [pairs][kpCapR]: the row-sorted right keypoints as (x, minr | maxr << 16, index, octave)
 };
 cudaError_t stereo_configure(int rows);
 cudaError_t launch_stereo(const LevelTable &T, const LevelTable *dT, const StereoArgs &A, int maxKp, cudaStream_t s);

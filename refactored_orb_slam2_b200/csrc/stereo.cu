@@ -1,14 +1,21 @@
 // Frame::ComputeStereoMatches (Frame.cc:477-646) on the device-resident outputs of two extract calls.
 //
 // k_stereo_rows — one CTA per pair: counting sort of the right keypoints by image row (int)yR
-//     (histogram, scan, scatter), the device form of the reference's vRowIndices table.
+//     (histogram, scan, scatter), the device form of the reference's vRowIndices table.  The sorted
+//     table holds 16-byte RECORDS (x, row reach minr / maxr, index, octave), everything the candidate
+//     gates need, so the match kernel reads one record per candidate instead of chasing
+//     index -> keypoint.
 // k_stereo_match — one warp per LEFT keypoint:
 //   * candidate scan.  The reference scans the bucket of row (size_t)vL in ascending iR; a right
 //     keypoint belongs to that bucket iff floor(yR - r) <= row <= ceil(yR + r), r = 2*scale[octR]
 //     (Frame.cc:493-502).  Lanes stride over the sorted right keypoints whose own row lies within
 //     +-(ceil(2*scale_max) + 2) of the left row (a superset), apply that exact predicate plus the
-//     octave and u-range gates (Frame.cc:540-545) and keep their minimum; a shuffle reduction on
-//     (distance, iR) lexicographic order reproduces the sequential strict-'<' scan.
+//     octave and u-range gates (Frame.cc:540-545) on up to 128 records per trip (four independent
+//     128-bit loads per lane), compact the survivors (about one candidate in five) into the warp's
+//     shared-memory list by ballot, and only then read descriptors — one per lane, all in flight at
+//     once; a shuffle reduction on (distance, iR) lexicographic order reproduces the sequential
+//     strict-'<' scan.  The kernel is bound by memory latency: this keeps the dependent loads per
+//     keypoint at bucket bounds -> records -> descriptors -> patches.
 //   * 11 x 11 SAD at 11 offsets on the keypoint's pyramid level (Frame.cc:557-600): patches are
 //     centre-subtracted integers, the L1 norm is exact in int; lanes split the 121 pixels.
 //   * parabola fit, disparity and depth in the reference's float order with _rn intrinsics
@@ -45,9 +52,10 @@ __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const 
 #endif
 constexpr int kWarps = ORBGPU_STEREO_WARPS;
 
-// rowStart[pair][rows + 1], sorted[pair][kpCapR]: right keypoint indices grouped by (int)y
+// rowStart[pair][rows + 1], recs[pair][kpCapR]: right keypoints grouped by (int)y as
+// (x bits, minr | maxr << 16, iR, octave) with minr / maxr = floor(yR - r) / ceil(yR + r), r = 2 * scale[octave] (Frame.cc:493-502)
 __global__ void __launch_bounds__(256)
-k_stereo_rows(StereoArgs A, int rows) {
+k_stereo_rows(const LevelTable *__restrict__ T, StereoArgs A, int rows) {
   extern __shared__ int sHist[];                 // rows + 1 counters, then a running cursor per row
   __shared__ int sWarpSum[8];
   const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -55,7 +63,7 @@ k_stereo_rows(StereoArgs A, int rows) {
   const int nR = A.cntR[imgR];
   const orbgpu_keypoint *kR = A.kpsR + (size_t)imgR * A.kpCapR;
   int *rowStart = A.rowStart + (size_t)pair * (rows + 1);
-  int *sorted = A.sorted + (size_t)pair * A.kpCapR;
+  int4 *recs = A.recs + (size_t)pair * A.kpCapR;
   for (int i = tid; i <= rows; i += 256) sHist[i] = 0;
   __syncthreads();
   for (int i = tid; i < nR; i += 256) atomicAdd(&sHist[min(max((int)kR[i].y, 0), rows - 1)], 1);
@@ -79,13 +87,16 @@ k_stereo_rows(StereoArgs A, int rows) {
   for (int i = lo; i < hi; i++) { const int v = sHist[i]; sHist[i] = run; rowStart[i] = run; run += v; }
   __syncthreads();
   for (int i = tid; i < nR; i += 256) {
-    const int r = min(max((int)kR[i].y, 0), rows - 1);
-    sorted[atomicAdd(&sHist[r], 1)] = i;
+    const orbgpu_keypoint kr = kR[i];
+    const int row = min(max((int)kr.y, 0), rows - 1);
+    const float r = __fmul_rn(2.0f, T->lv[kr.octave].scale);
+    const int maxr = (int)ceilf(__fadd_rn(kr.y, r)), minr = (int)floorf(__fsub_rn(kr.y, r));
+    recs[atomicAdd(&sHist[row], 1)] = make_int4(__float_as_int(kr.x), (minr & 0xffff) | (maxr << 16), i, kr.octave);
   }
 }
 
 #ifndef ORBGPU_STEREO_MIN_CTAS
-#define ORBGPU_STEREO_MIN_CTAS 24     // 40 registers: the kernel is latency bound, 48 instead of 36 resident warps (0.64 -> 0.59 ms per 320 pairs)
+#define ORBGPU_STEREO_MIN_CTAS 20     // 48 registers, 40 resident warps: 16 / 20 / 24 CTAs per SM (64 / 48 / 40 registers, the last with spills) measured 0.523 / 0.483 / 0.494 ms per 320 pairs
 #endif
 __global__ void __launch_bounds__(kWarps * 32, ORBGPU_STEREO_MIN_CTAS)
 k_stereo_match(const LevelTable *__restrict__ T, StereoArgs A, int rows, int rowReach) {
@@ -97,11 +108,12 @@ k_stereo_match(const LevelTable *__restrict__ T, StereoArgs A, int rows, int row
   if (iL >= nL) return;
   const size_t outIdx = (size_t)pair * A.kpCapL + iL;
   const orbgpu_keypoint *kL = A.kpsL + (size_t)imgL * A.kpCapL;
-  const orbgpu_keypoint *kR = A.kpsR + (size_t)imgR * A.kpCapR;
   const uint4 *dL = reinterpret_cast<const uint4 *>(A.descL + ((size_t)imgL * A.kpCapL + iL) * 32);
   const uint4 *dR = reinterpret_cast<const uint4 *>(A.descR + (size_t)imgR * A.kpCapR * 32);
   const int *rowStart = A.rowStart + (size_t)pair * (rows + 1);
-  const int *sorted = A.sorted + (size_t)pair * A.kpCapR;
+  const int4 *recs = A.recs + (size_t)pair * A.kpCapR;
+  __shared__ int2 sCand[kWarps][128];            // gate survivors of one trip: (iR, x bits)
+  int2 *cand = sCand[threadIdx.x >> 5];
 
   float uRight = -1.0f, depth = -1.0f;
   int sadOut = -1;
@@ -113,32 +125,50 @@ k_stereo_match(const LevelTable *__restrict__ T, StereoArgs A, int rows, int row
   const float minD = 0.f, maxD = __fdiv_rn(A.mbf, A.mb);
   const float minU = __fsub_rn(uL, maxD), maxU = __fsub_rn(uL, minD);
 
-  int bestDist = kThHigh, bestR = 0x7fffffff;
+  int bestDist = kThHigh, bestR = 0x7fffffff, bestX = 0;
   if (!(maxU < 0)) {
     const uint4 a0 = dL[0], a1 = dL[1];
     const int cLo = rowStart[min(max(rowL - rowReach, 0), rows)], cHi = rowStart[min(max(rowL + rowReach + 1, 0), rows)];
-    for (int c = cLo + lane; c < cHi; c += 32) {
-      const int iR = sorted[c];
-      const orbgpu_keypoint kr = kR[iR];
-      const float r = __fmul_rn(2.0f, T->lv[kr.octave].scale);
-      const int maxr = (int)ceilf(__fadd_rn(kr.y, r)), minr = (int)floorf(__fsub_rn(kr.y, r));
-      if (rowL < minr || rowL > maxr) continue;
-      if (kr.octave < levelL - 1 || kr.octave > levelL + 1) continue;
-      if (!(kr.x >= minU && kr.x <= maxU)) continue;
-      const int d = hamming256(a0, a1, dR[2 * iR], dR[2 * iR + 1]);
-      if (d < bestDist || (d == bestDist && iR < bestR)) { bestDist = d; bestR = iR; }
+    const unsigned below = (1u << lane) - 1u;
+    for (int c0 = cLo; c0 < cHi; c0 += 128) {
+      int n = 0;                                  // survivors of this trip (warp-uniform)
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int c = c0 + 32 * u + lane;
+        bool ok = false;
+        int4 rc = make_int4(0, 0, 0, 0);
+        if (c < cHi) {
+          rc = recs[c];
+          const int minr = (int)(short)(rc.y & 0xffff), maxr = rc.y >> 16;
+          const float x = __int_as_float(rc.x);
+          ok = rowL >= minr && rowL <= maxr && rc.w >= levelL - 1 && rc.w <= levelL + 1 && x >= minU && x <= maxU;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) cand[n + __popc(m & below)] = make_int2(rc.z, rc.x);
+        n += __popc(m);
+      }
+      __syncwarp();
+      for (int j = lane; j < n; j += 32) {
+        const int2 cd = cand[j];
+        const int d = hamming256(a0, a1, dR[2 * cd.x], dR[2 * cd.x + 1]);
+        if (d < bestDist || (d == bestDist && cd.x < bestR)) { bestDist = d; bestR = cd.x; bestX = cd.y; }
+      }
+      __syncwarp();
     }
   }
+  const int myDist = bestDist, myR = bestR;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const int od = __shfl_xor_sync(0xffffffffu, bestDist, o);
     const int orr = __shfl_xor_sync(0xffffffffu, bestR, o);
     if (od < bestDist || (od == bestDist && orr < bestR)) { bestDist = od; bestR = orr; }
   }
+  // x of the winner from the lane that found it (bestR = 0x7fffffff on every lane when nothing passed the gates)
+  const unsigned owner = __ballot_sync(0xffffffffu, myDist == bestDist && myR == bestR);
+  const float uR0 = __int_as_float(__shfl_sync(0xffffffffu, bestX, __ffs((int)owner) - 1));
 
   if (bestDist < (kThHigh + kThLow) / 2) {
     const LevelGeom &G = T->lv[levelL];
-    const float uR0 = kR[bestR].x;
     const float sf = G.invScale;
     const float suL = roundf(__fmul_rn(kp.x, sf)), svL = roundf(__fmul_rn(kp.y, sf));
     const float suR0 = roundf(__fmul_rn(uR0, sf));
@@ -170,24 +200,25 @@ k_stereo_match(const LevelTable *__restrict__ T, StereoArgs A, int rows, int row
           if (lane + 32 * t < 121) sad = __sad(lv[t] + centreR, (int)PR[off[t] + inc], sad);
         part[inc + L] = sad;
       }
+      // best shift (first minimum, Frame.cc:586-590) and its two neighbours for the parabola, tracked while the sums arrive:
+      // no indexed array, everything stays in registers
       int best = 0x7fffffff, bestInc = 0;
-      float dist[11];
+      float prev = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+      bool justBest = false;
+      auto visit = [&](int k, int sv) {
+        const float f = (float)sv;
+        if (justBest) d3 = f;
+        justBest = sv < best;
+        if (justBest) { best = sv; bestInc = k - L; d1 = prev; d2 = f; }
+        prev = f;
+      };
 #pragma unroll
       for (int k = 0; k < 6; k++) {
         const unsigned both = __reduce_add_sync(0xffffffffu, part[2 * k] | (k < 5 ? part[2 * k + 1] << 16 : 0u));
-        const int s0 = (int)(both & 0xffffu), s1 = (int)(both >> 16);
-        dist[2 * k] = (float)s0;
-        if (s0 < best) { best = s0; bestInc = 2 * k - L; }
-        if (k < 5) {
-          dist[2 * k + 1] = (float)s1;
-          if (s1 < best) { best = s1; bestInc = 2 * k + 1 - L; }
-        }
+        visit(2 * k, (int)(both & 0xffffu));
+        if (k < 5) visit(2 * k + 1, (int)(both >> 16));
       }
       if (!(bestInc == -L || bestInc == L)) {
-        float d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-        for (int k = 1; k < 10; k++)
-          if (k == bestInc + L) { d1 = dist[k - 1]; d2 = dist[k]; d3 = dist[k + 1]; }
         const float deltaR = __fdiv_rn(__fsub_rn(d1, d3),
                                        __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
         if (!(deltaR < -1 || deltaR > 1)) {
@@ -273,7 +304,7 @@ cudaError_t VNAME(launch_stereo)(const LevelTable &T, const LevelTable *dT, cons
   const int rows = T.lv[0].h;
   // a right keypoint at row yR reaches rows floor(yR - r) .. ceil(yR + r), r <= 2 * scale of the top level
   const int rowReach = (int)std::ceil(2.0f * T.lv[T.nlevels - 1].scale) + 2;
-  k_stereo_rows<<<A.pairs, 256, (rows + 1) * sizeof(int), s>>>(A, rows);
+  k_stereo_rows<<<A.pairs, 256, (rows + 1) * sizeof(int), s>>>(dT, A, rows);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -7,7 +7,7 @@ import json,sys
 d=json.loads(sys.stdin.read())
 print('$1', 'device', round(d['value']), 'e2e', round(d['e2e']['value']), 'single_call', round(d['e2e']['single_call_value']))"
 }
+BENCH_PIPELINE_DEPTH=2 run depth2 | tee -a "$out"
 BENCH_PIPELINE_DEPTH=3 run depth3 | tee -a "$out"
-ORBGPU_CHUNKS=1 run chunks1 | tee -a "$out"
-ORBGPU_CHUNKS=4 run chunks4 | tee -a "$out"
-BENCH_PIPELINE_DEPTH=3 ORBGPU_CHUNKS=4 run depth3_chunks4 | tee -a "$out"
+BENCH_PIPELINE_DEPTH=4 run depth4 | tee -a "$out"
+BENCH_PIPELINE_DEPTH=3 ORBGPU_CHUNKS=1 run depth3_chunks1 | tee -a "$out"

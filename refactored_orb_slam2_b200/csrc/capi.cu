@@ -73,7 +73,7 @@ struct orbgpu_extractor {
   TmaMaps blurMaps{}, rzMaps{}, descDiscMaps{}, descPatchMaps{};
   int4 *dRzTiles = nullptr; size_t rzTilesCap = 0; int rzTileOff[kMaxLevels] = {}, rzTileCnt[kMaxLevels] = {};
   int rzSlotBytes = 0;
-  int4 *dBlurTiles = nullptr; size_t blurTilesCap = 0; int nBlurTiles = 0;
+  int4 *dBlurTiles = nullptr; size_t blurTilesCap = 0; int nBlurTiles = 0, nBlurTiles0 = 0;   // tiles are level-major: the first nBlurTiles0 are level 0
   int octSmem = 0;
 
   // buffers (sized for max_width x max_height x max_batch)
@@ -90,7 +90,7 @@ struct orbgpu_extractor {
   cudaEvent_t evDone = nullptr;
   // the blur of a batch only needs its pyramid: it runs on a side stream next to FAST + octree and joins before describe
   cudaStream_t side = nullptr;
-  cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr, evLevel0 = nullptr;
   int lastBatch = 0;
   // CUDA graph of the extraction kernel sequence for small batches (the frame-at-a-time path is launch bound: 13 kernels
   // and 2 memsets for one stereo pair); re-captured whenever its key changes
@@ -322,6 +322,7 @@ int configure(orbgpu_extractor *e, int w, int h) {
   }
   e->T = T; e->ntiles = nPlainStrips; e->ntilesShift = (int)tiles.size() - nPlainStrips; e->fastCfg = fc; e->octSmem = octSmem;
   e->blurMaps = blurMaps; e->nBlurTiles = (int)blurTiles.size();
+  e->nBlurTiles0 = (int)std::count_if(blurTiles.begin(), blurTiles.end(), [](const int4 &t) { return t.x == 0; });
   e->descDiscMaps = discMaps; e->descPatchMaps = patchMaps;
   e->rzMaps = rzMaps; e->rzSlotBytes = rzSlot;
   for (int l = 0; l < kMaxLevels; l++) { e->rzTileOff[l] = rzOff[l]; e->rzTileCnt[l] = rzCnt[l]; }
@@ -363,14 +364,25 @@ int run_extract_range(orbgpu_extractor *e, const uint8_t *dImages, int imgBase, 
     return ORBGPU_OK;
   };
   if (overlap) {
+    // Level 0 is final after the import: its blur (46 % of the blur's pixels) starts at once on the side stream and runs next to the
+    // seven dependent resize launches, whose upper levels are too small to fill the GPU; the blur of levels 1 .. 7 follows on the
+    // side stream when FAST has finished (next to the octree) and joins before the descriptors.
+    static const bool noSplit = getenv("ORBGPU_NO_BLUR_SPLIT") != nullptr;
+    const int n0 = noSplit || e->T.nlevels < 2 ? 0 : e->nBlurTiles0;
     ORBGPU_CUDA_CHECK(launch_import_level0(e->T, B, dImages, rowStep, imgStep, imgBase, batch, s));
+    if (n0 > 0) {
+      ORBGPU_CUDA_CHECK(cudaEventRecord(e->evLevel0, s));
+      ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(e->side, e->evLevel0, 0));
+      ORBGPU_CUDA_CHECK(launch_blur(e->T, B, e->blurMaps, e->dBlurTiles, n0, imgBase, batch, e->side));
+    }
     int rc = pyramid_rest(s);
     if (rc) return rc;
     ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->dTiles, e->ntiles, e->ntilesShift, e->fastCfg, imgBase, batch, s));
     ORBGPU_CUDA_CHECK(cudaEventRecord(e->evFork, s));
     ORBGPU_CUDA_CHECK(lat ? launch_octree_lat(e->T, B, imgBase, batch, e->octSmem, s) : launch_octree(e->T, B, imgBase, batch, e->octSmem, s));
-    ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(e->side, e->evFork, 0));     // the octree's CTAs are placed first, the blur fills the rest
-    ORBGPU_CUDA_CHECK(launch_blur(e->T, B, e->blurMaps, e->dBlurTiles, e->nBlurTiles, imgBase, batch, e->side));
+    ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(e->side, e->evFork, 0));
+    if (e->nBlurTiles > n0)
+      ORBGPU_CUDA_CHECK(launch_blur(e->T, B, e->blurMaps, e->dBlurTiles + n0, e->nBlurTiles - n0, imgBase, batch, e->side));
     ORBGPU_CUDA_CHECK(cudaEventRecord(e->evJoin, e->side));
     ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(s, e->evJoin, 0));
     ORBGPU_CUDA_CHECK(lat ? launch_describe_lat(e->T, B, e->descDiscMaps, e->descPatchMaps, imgBase, batch, s) : launch_describe(e->T, B, e->descDiscMaps, e->descPatchMaps, imgBase, batch, s));
@@ -539,6 +551,7 @@ int orbgpu_extractor_create(const orbgpu_extractor_params *params, orbgpu_extrac
   ORBGPU_CUDA_CHECK(describe_prepare_lat());
   ORBGPU_CUDA_CHECK(cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming));
   ORBGPU_CUDA_CHECK(cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming));
+  ORBGPU_CUDA_CHECK(cudaEventCreateWithFlags(&e->evLevel0, cudaEventDisableTiming));
   LevelTable T;
   std::vector<int2> tabs;
   std::vector<int4> tiles;
@@ -579,6 +592,7 @@ void orbgpu_extractor_destroy(orbgpu_extractor *e) {
   if (e->evDone) cudaEventDestroy(e->evDone);
   if (e->evFork) cudaEventDestroy(e->evFork);
   if (e->evJoin) cudaEventDestroy(e->evJoin);
+  if (e->evLevel0) cudaEventDestroy(e->evLevel0);
   if (e->side) cudaStreamDestroy(e->side);
   for (cudaEvent_t ev : e->evChunkIn) if (ev) cudaEventDestroy(ev);
   for (cudaEvent_t ev : e->evChunkDone) if (ev) cudaEventDestroy(ev);

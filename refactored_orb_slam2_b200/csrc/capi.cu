@@ -368,7 +368,7 @@ int run_extract_range(orbgpu_extractor *e, const uint8_t *dImages, int imgBase, 
     // seven dependent resize launches, whose upper levels are too small to fill the GPU; the blur of levels 1 .. 7 follows on the
     // side stream when FAST has finished (next to the octree) and joins before the descriptors.
     static const bool noSplit = getenv("ORBGPU_NO_BLUR_SPLIT") != nullptr;
-    const int n0 = noSplit || e->T.nlevels < 2 ? 0 : e->nBlurTiles0;
+    const int n0 = noSplit || lat || e->T.nlevels < 2 ? 0 : e->nBlurTiles0;      // frame-at-a-time calls are launch bound: one blur launch
     ORBGPU_CUDA_CHECK(launch_import_level0(e->T, B, dImages, rowStep, imgStep, imgBase, batch, s));
     if (n0 > 0) {
       ORBGPU_CUDA_CHECK(cudaEventRecord(e->evLevel0, s));
@@ -377,7 +377,16 @@ int run_extract_range(orbgpu_extractor *e, const uint8_t *dImages, int imgBase, 
     }
     int rc = pyramid_rest(s);
     if (rc) return rc;
-    ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->dTiles, e->ntiles, e->ntilesShift, e->fastCfg, imgBase, batch, s));
+    if (lat && e->ntiles > 0 && e->ntilesShift > 0) {
+      // frame-at-a-time: the plain and the shifted FAST launch run side by side (each is one ~8 us march deep whatever its size)
+      ORBGPU_CUDA_CHECK(cudaEventRecord(e->evLevel0, s));
+      ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(e->side, e->evLevel0, 0));
+      ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->dTiles, e->ntiles, e->ntilesShift, e->fastCfg, imgBase, batch, s, e->side));
+      ORBGPU_CUDA_CHECK(cudaEventRecord(e->evJoin, e->side));
+      ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(s, e->evJoin, 0));
+    } else {
+      ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->dTiles, e->ntiles, e->ntilesShift, e->fastCfg, imgBase, batch, s, s));
+    }
     ORBGPU_CUDA_CHECK(cudaEventRecord(e->evFork, s));
     ORBGPU_CUDA_CHECK(lat ? launch_octree_lat(e->T, B, imgBase, batch, e->octSmem, s) : launch_octree(e->T, B, imgBase, batch, e->octSmem, s));
     ORBGPU_CUDA_CHECK(cudaStreamWaitEvent(e->side, e->evFork, 0));
@@ -394,7 +403,7 @@ int run_extract_range(orbgpu_extractor *e, const uint8_t *dImages, int imgBase, 
     int rc = pyramid_rest(s);
     if (rc) return rc;
   }
-  { StageTimer t(e, 1); ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->dTiles, e->ntiles, e->ntilesShift, e->fastCfg, imgBase, batch, s)); }
+  { StageTimer t(e, 1); ORBGPU_CUDA_CHECK(launch_fast(e->T, B, e->dTiles, e->ntiles, e->ntilesShift, e->fastCfg, imgBase, batch, s, s)); }
   { StageTimer t(e, 2); ORBGPU_CUDA_CHECK(lat ? launch_octree_lat(e->T, B, imgBase, batch, e->octSmem, s) : launch_octree(e->T, B, imgBase, batch, e->octSmem, s)); }
   { StageTimer t(e, 3); ORBGPU_CUDA_CHECK(launch_blur(e->T, B, e->blurMaps, e->dBlurTiles, e->nBlurTiles, imgBase, batch, s)); }
   { StageTimer t(e, 4); ORBGPU_CUDA_CHECK(lat ? launch_describe_lat(e->T, B, e->descDiscMaps, e->descPatchMaps, imgBase, batch, s) : launch_describe(e->T, B, e->descDiscMaps, e->descPatchMaps, imgBase, batch, s)); }

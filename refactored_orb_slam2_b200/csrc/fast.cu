@@ -406,8 +406,9 @@ cudaError_t fast_configure(int smemBytes) {
 }
 
 // strips[0 .. nPlain) run in the plain form, strips[nPlain .. nPlain + nShift) in the shifted form (fast_strip_shifted)
+// (on stream sShift: frame-at-a-time calls run the two launches side by side, a march is ~8 us long whatever the batch)
 cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const int4 *strips, int nPlain, int nShift, const FastConfig &c,
-                        int imgBase, int batch, cudaStream_t s) {
+                        int imgBase, int batch, cudaStream_t s, cudaStream_t sShift) {
   const FmaConsts K{0xffffffffu, 256u};
   if (nPlain > 0) {
     const int total = nPlain * batch;
@@ -417,7 +418,7 @@ cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const int4
   }
   if (nShift > 0) {
     const int total = nShift * batch;
-    k_fast_strips<true><<<(total + kWarps - 1) / kWarps, kThreads, c.smemBytes, s>>>(B.dT, strips + nPlain, nShift, total, imgBase, B.pyr, B.cand, B.candCount,
+    k_fast_strips<true><<<(total + kWarps - 1) / kWarps, kThreads, c.smemBytes, sShift>>>(B.dT, strips + nPlain, nShift, total, imgBase, B.pyr, B.cand, B.candCount,
                                                                                        B.status, c.stageCap, c.rowsCap, K);
     count_launch();
   }

@@ -140,7 +140,7 @@ int fast_cells_per_strip(int wCell);
 FastConfig fast_make_config(const LevelTable &T);
 bool fast_strip_shifted(const LevelGeom &G, int firstCell, int cells);
 cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const int4 *strips, int nPlain, int nShift, const FastConfig &c,
-                        int imgBase, int batch, cudaStream_t s);
+                        int imgBase, int batch, cudaStream_t s, cudaStream_t sShift);
 cudaError_t launch_octree(const LevelTable &T, const ExtractBuffers &B, int imgBase, int batch, int smemBytes,
                           cudaStream_t s);
 int hamming_dense_q(int nq);

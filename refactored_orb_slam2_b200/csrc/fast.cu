@@ -43,7 +43,7 @@ __device__ __forceinline__ unsigned mx2(unsigned a, unsigned b) { return __vmaxs
 // right shift are therefore written as integer multiply-adds, which issue on the otherwise idle FMA pipe:
 // ~x = x * -1 + -1  and  x >> 24 = hi32(x * 256).  The multipliers arrive as kernel arguments (FmaConsts) — with literal
 // constants ptxas folds both back into IADD3 / SHF on the ALU pipe.
-struct FmaConsts { unsigned ones, two8; };          // 0xffffffff, 256
+struct FmaConsts { unsigned ones, two8, zero; };          // 0xffffffff, 256, 0
 __device__ __forceinline__ unsigned not_fma(unsigned x, const FmaConsts &K) { return x * K.ones + K.ones; }
 __device__ __forceinline__ unsigned top_byte_fma(unsigned x, const FmaConsts &K) { return __umulhi(x, K.two8); }
 
@@ -209,9 +209,16 @@ __device__ __forceinline__ void march_strip(const uint8_t *rowPtr, int pitch, in
     for (int k = 0; k < 7; k++) {
       const int r = r0 + k;
       if (r < nRows) {
-        raw[(k + kAhead) % 7] = load_row<kShift>(rowPtr + kAhead * pitch);       // row r + kAhead (always inside the padded plane)
-        prefetch_l1(rowPtr + (kAhead + kPrefetchRows) * pitch + pfOff);          // and later rows on their way from HBM / L2 into L1
-        rowPtr += pitch;
+        // The address of the row requested now is tied to the DATA of the row unpacked now (dep = w0 * 0, the zero a kernel argument
+        // so that it survives ptxas).  ptxas tags the three loads of a row with one scoreboard and reuses it every other step; with
+        // the new loads hoisted above the unpack, the unpack's wait for row r also waited for the loads just issued — a full memory
+        // round trip in three of the seven unrolled steps, 15 % of the kernel's stall samples (profiles/r2_fast_stall_sites.txt).
+        // With the dependence the request cannot be issued before row r has arrived (it has: it was requested a step ago).
+        static_assert(kAhead == 1, "the dependence ties row r + 1 to row r");
+        const unsigned dep = raw[k].w0 * K.zero;
+        rowPtr += pitch + (int)dep;                                              // row r + 1 (always inside the padded plane)
+        raw[(k + 1) % 7] = load_row<kShift>(rowPtr);
+        prefetch_l1(rowPtr + kPrefetchRows * pitch + pfOff);                     // and later rows on their way from HBM / L2 into L1
         unpack_row<kShift>(raw[k], win[k], K);
         if (r >= 6) {
           // pixel row y = r - 6: its ring rows y-3 .. y+3 are the source rows r-6 .. r = slots (k + 1 + i) % 7
@@ -409,7 +416,7 @@ cudaError_t fast_configure(int smemBytes) {
 // (on stream sShift: frame-at-a-time calls run the two launches side by side, a march is ~8 us long whatever the batch)
 cudaError_t launch_fast(const LevelTable &T, const ExtractBuffers &B, const int4 *strips, int nPlain, int nShift, const FastConfig &c,
                         int imgBase, int batch, cudaStream_t s, cudaStream_t sShift) {
-  const FmaConsts K{0xffffffffu, 256u};
+  const FmaConsts K{0xffffffffu, 256u, 0u};
   if (nPlain > 0) {
     const int total = nPlain * batch;
     k_fast_strips<false><<<(total + kWarps - 1) / kWarps, kThreads, c.smemBytes, s>>>(B.dT, strips, nPlain, total, imgBase, B.pyr, B.cand, B.candCount,

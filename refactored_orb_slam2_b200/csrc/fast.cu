@@ -214,11 +214,10 @@ __device__ __forceinline__ void march_strip(const uint8_t *rowPtr, int pitch, in
         // the new loads hoisted above the unpack, the unpack's wait for row r also waited for the loads just issued — a full memory
         // round trip in three of the seven unrolled steps, 15 % of the kernel's stall samples (profiles/r2_fast_stall_sites.txt).
         // With the dependence the request cannot be issued before row r has arrived (it has: it was requested a step ago).
-        static_assert(kAhead == 1, "the dependence ties row r + 1 to row r");
         const unsigned dep = raw[k].w0 * K.zero;
-        rowPtr += pitch + (int)dep;                                              // row r + 1 (always inside the padded plane)
-        raw[(k + 1) % 7] = load_row<kShift>(rowPtr);
-        prefetch_l1(rowPtr + kPrefetchRows * pitch + pfOff);                     // and later rows on their way from HBM / L2 into L1
+        rowPtr += pitch + (int)dep;                                              // row r + 1
+        raw[(k + kAhead) % 7] = load_row<kShift>(rowPtr + (kAhead - 1) * pitch);   // row r + kAhead (always inside the padded plane)
+        prefetch_l1(rowPtr + (kAhead - 1 + kPrefetchRows) * pitch + pfOff);      // and later rows on their way from HBM / L2 into L1
         unpack_row<kShift>(raw[k], win[k], K);
         if (r >= 6) {
           // pixel row y = r - 6: its ring rows y-3 .. y+3 are the source rows r-6 .. r = slots (k + 1 + i) % 7
@@ -345,20 +344,25 @@ k_fast_strips(const LevelTable *__restrict__ T, const int4 *__restrict__ strips,
   iniMask = __reduce_or_sync(0xffffffffu, iniMask);
   int *counter = &candCount[img * kMaxLevels + level];
   Cand *out = cand + G.candOffset + (size_t)img * G.candCap;
+  // one global atomic per STRIP: the entries that qualify are counted first, the strip's range of the level's list is claimed
+  // once, and a second pass writes (an atomic per 32 entries made every pass wait for its own round trip to L2)
+  auto qualifies = [&](unsigned e) {
+    const int x = (int)(e & 127u), c = (x >= wCell) + (x >= 2 * wCell) + (x >= 3 * wCell);
+    return (int)((e >> 13) & 0xffu) > iniS || !((iniMask >> c) & 1u);
+  };
+  int mine = 0;
+  for (int i = lane; i < nk; i += 32) mine += qualifies(stage[i]) ? 1 : 0;
+  const int total = __reduce_add_sync(0xffffffffu, mine);
+  if (total == 0) return;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(counter, total);
+  base = __shfl_sync(0xffffffffu, base, 0);
   for (int i0 = 0; i0 < nk; i0 += 32) {
     const int i = i0 + lane;
     unsigned e = 0u;
     bool emit = false;
-    if (i < nk) {
-      e = stage[i];
-      const int x = (int)(e & 127u), c = (x >= wCell) + (x >= 2 * wCell) + (x >= 3 * wCell);
-      emit = (int)((e >> 13) & 0xffu) > iniS || !((iniMask >> c) & 1u);
-    }
+    if (i < nk) { e = stage[i]; emit = qualifies(e); }
     const unsigned mask = __ballot_sync(0xffffffffu, emit);
-    if (mask == 0u) continue;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(counter, __popc(mask));
-    base = __shfl_sync(0xffffffffu, base, 0);
     if (emit) {
       const int slot = base + __popc(mask & ((1u << lane) - 1u));
       Cand o;
@@ -366,6 +370,7 @@ k_fast_strips(const LevelTable *__restrict__ T, const int4 *__restrict__ strips,
       o.resp = ((e >> 13) & 0xffu) + (unsigned)minTh - 1u;             // cv::FAST response = margin - 1
       if (slot < G.candCap) out[slot] = o; else atomicOr(status, kStatusCandOverflow);
     }
+    base += __popc(mask);
   }
 }
 

@@ -153,44 +153,49 @@ __device__ __forceinline__ int dp4a_us(unsigned data, unsigned weights, int acc)
   return d;
 }
 
-// blockIdx.x = chunk of 2 * kWarpsPerCta output slots (level-major keypoint index), blockIdx.y = image
+// CTAs of one image are numbered level by level: level l owns CTAs ctaStart[l] .. ctaStart[l + 1) (ceil(selCap / keypoints per
+// CTA) each), so a warp knows its (level, node) from blockIdx alone and requests the node's record at once; the level's start
+// in the level-major output only matters for the final stores.
+struct DescribeCtas { int ctaStart[kMaxLevels + 1]; };
+
+// blockIdx.x = CTA of the image (see DescribeCtas), blockIdx.y = image
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-k_describe(const __grid_constant__ TmaMaps pyrMaps, const __grid_constant__ TmaMaps blurMaps, const LevelTable *__restrict__ T,
-           const int4 *__restrict__ selAll, const int *__restrict__ selCount, orbgpu_keypoint *__restrict__ kps,
-           uint8_t *__restrict__ desc, int *__restrict__ kpCount, unsigned *__restrict__ status, int imgBase) {
+k_describe(const __grid_constant__ TmaMaps pyrMaps, const __grid_constant__ TmaMaps blurMaps, const __grid_constant__ DescribeCtas ctas,
+           const LevelTable *__restrict__ T, const int4 *__restrict__ selAll, const int *__restrict__ selCount,
+           orbgpu_keypoint *__restrict__ kps, uint8_t *__restrict__ desc, int *__restrict__ kpCount, unsigned *__restrict__ status,
+           int imgBase) {
   extern __shared__ uint8_t smemRaw[];
   __shared__ __align__(8) unsigned long long sBar[kWarpsPerCta];
 
   const int img = imgBase + blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int half = lane >> 4, l16 = lane & 15;
-  const int slot0 = (blockIdx.x * kWarpsPerCta + warp) * kKpPerWarp;    // output row of the warp's first keypoint
-  // the image's output rows are level-major: lane l holds the end (exclusive) of level l's rows after a warp scan of the
-  // per-level octree counts; a keypoint's level is the number of levels that end at or before its slot
   const int nlevels = T->nlevels;
-  int levelEnd = lane < nlevels ? selCount[img * kMaxLevels + lane] : 0;
+  int level = 0;
 #pragma unroll
-  for (int o = 1; o < kMaxLevels; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, levelEnd, o);
-    if (lane >= o) levelEnd += v;
-  }
-  const int total = __shfl_sync(0xffffffffu, levelEnd, nlevels - 1);
+  for (int l = 1; l < kMaxLevels; l++) level += (l < nlevels && (int)blockIdx.x >= ctas.ctaStart[l]) ? 1 : 0;
+  const LevelGeom &G = T->lv[level];
+  const int i0 = (((int)blockIdx.x - ctas.ctaStart[level]) * kWarpsPerCta + warp) * kKpPerWarp;    // the warp's first node of the level
+  // two independent requests: the per-level octree counts (lane l holds level l's) and the node's record
+  const int cnt = lane < nlevels ? selCount[img * kMaxLevels + lane] : 0;
+  int4 s = selAll[G.selOffset + (size_t)img * G.selCap + min(i0 + half, G.selCap - 1)];   // x_level, y_level, response
+  // the image's output rows are level-major: this level starts behind the lower levels' counts
+  const int total = __reduce_add_sync(0xffffffffu, cnt);
+  const int start = __reduce_add_sync(0xffffffffu, lane < level ? cnt : 0);
+  const int levelCount = __shfl_sync(0xffffffffu, cnt, level);
   const int kpCap = T->kpCap;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     kpCount[img] = min(total, kpCap);
     if (total > kpCap) atomicOr(status, kStatusKpOverflow);
   }
-  const int limit = min(total, kpCap);
-  if (slot0 >= limit) return;                                           // warp-uniform
-  const bool live = slot0 + half < limit;
-  const int slot = live ? slot0 + half : slot0;                         // an idle second half repeats the first keypoint and stores nothing
-  const int lvA = __popc(__ballot_sync(0xffffffffu, lane < nlevels && slot0 >= levelEnd));
-  const int lvB = __popc(__ballot_sync(0xffffffffu, lane < nlevels && slot0 + 1 >= levelEnd));
-  const int level = min(live && half ? lvB : lvA, nlevels - 1);
-  const int startSrc = __shfl_sync(0xffffffffu, levelEnd, max(level - 1, 0));
-  const int start = level ? startSrc : 0;
-  const LevelGeom &G = T->lv[level];
-  const int4 s = selAll[G.selOffset + (size_t)img * G.selCap + (slot - start)];   // x_level, y_level, response
+  if (i0 >= levelCount || start + i0 >= kpCap) return;                  // warp-uniform
+  const bool live = i0 + half < levelCount && start + i0 + half < kpCap;
+  {
+    // an idle second half repeats the first keypoint and stores nothing
+    const int x0 = __shfl_sync(0xffffffffu, s.x, l16), y0 = __shfl_sync(0xffffffffu, s.y, l16), z0 = __shfl_sync(0xffffffffu, s.z, l16);
+    if (!live) { s.x = x0; s.y = y0; s.z = z0; }
+  }
+  const int slot = start + i0 + (live ? half : 0);                      // output row of this half's keypoint
 
   // ---- stage both neighbourhoods: two tensor copies per keypoint, no per-row address arithmetic, one memory latency
   uint8_t *disc = smemRaw + ((128u - (smem_u32(smemRaw) & 127u)) & 127u) + warp * kWarpSlot + half * kKpSlot;
@@ -359,9 +364,13 @@ cudaError_t VNAME(describe_configure)() {
 
 cudaError_t VNAME(launch_describe)(const LevelTable &T, const ExtractBuffers &B, const TmaMaps &pyrMaps, const TmaMaps &blurMaps, int imgBase,
                                    int batch, cudaStream_t s) {
-  dim3 grid((T.kpCap + kKpPerWarp * kWarpsPerCta - 1) / (kKpPerWarp * kWarpsPerCta), batch);
-  k_describe<<<grid, kWarpsPerCta * 32, VNAME(describe_smem_bytes)(), s>>>(pyrMaps, blurMaps, B.dT, B.sel, B.selCount, B.kps, B.desc, B.kpCount,
-                                                                          B.status, imgBase);
+  DescribeCtas ctas{};
+  const int perCta = kKpPerWarp * kWarpsPerCta;
+  for (int l = 0; l < T.nlevels; l++) ctas.ctaStart[l + 1] = ctas.ctaStart[l] + (T.lv[l].selCap + perCta - 1) / perCta;
+  for (int l = T.nlevels; l < kMaxLevels; l++) ctas.ctaStart[l + 1] = ctas.ctaStart[T.nlevels];
+  dim3 grid(ctas.ctaStart[T.nlevels], batch);
+  k_describe<<<grid, kWarpsPerCta * 32, VNAME(describe_smem_bytes)(), s>>>(pyrMaps, blurMaps, ctas, B.dT, B.sel, B.selCount, B.kps, B.desc,
+                                                                          B.kpCount, B.status, imgBase);
   count_launch();
   return cudaGetLastError();
 }

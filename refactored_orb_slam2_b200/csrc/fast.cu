@@ -20,9 +20,12 @@
 // step are then plain registers — the 3-input VIMNMX3.S16x2 arc networks (68 per pixel pair) are the only real work
 // left on the ALU pipe.  The loop is unrolled seven-fold so that the window rotates by register renaming.
 // Scores (margin - minTh, 0 = not a corner at minTh) stay in registers as well: NMS of row y-1 runs when row y is
-// scored, horizontal neighbours come from the adjacent lanes by shuffle, cell borders are per-lane constant masks,
-// survivors are appended to the warp's shared-memory stage list (4 bytes each), and at the end of the strip the warp
-// applies the per-cell threshold fallback and appends to the level's candidate list with one global atomic per 32.
+// scored, horizontal neighbours come from the adjacent lanes by shuffle, cell borders are per-lane constant masks, and the
+// row's decision leaves the loop as one word per lane (the four scores as bytes, zero where the pixel does not survive)
+// stored without a branch to the warp's score rows in shared memory.  After the march the lanes collect the non-zero bytes
+// into the warp's stage list (4 bytes per survivor), the warp applies the per-cell threshold fallback, claims its range of
+// the level's candidate list with one global atomic and writes it.  Strips of four 32-pixel cells start two bytes off the
+// 4-byte grid and run in the SHIFTED instantiation of the kernel (own launch, see unpack_row).
 // Candidate order in HBM is arbitrary: the octree only needs each candidate's position in the
 // reference's cell-major order to break response ties, and that is a function of (x, y).
 #include <cstdlib>
